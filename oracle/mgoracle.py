@@ -1,0 +1,238 @@
+"""ctypes binding of the CPU parity oracle (oracle/mg_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Nothing under saras_b200/
+may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+PRESSURE, RESIDUAL, TMP, SMOOTHED = 0, 1, 2, 3
+XIXX, XIX2, ETYY, ETY2, ZTZZ, ZTZ2 = range(6)
+HX, HY, HZ, HX2, HZ2, HZHX, HXHY, HYHZ, HXHYHZ = range(9)
+COEF_NAMES = ["hx", "hy", "hz", "hx2", "hz2", "hzhx", "hxhy", "hyhz", "hxhyhz"]
+METRIC_NAMES = ["xixx", "xix2", "etyy", "ety2", "ztzz", "ztz2"]
+
+
+class MgoParams(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int), ("test_poisson", C.c_int),
+        ("xInd", C.c_int), ("yInd", C.c_int), ("zInd", C.c_int),
+        ("npX", C.c_int), ("npY", C.c_int),
+        ("xPer", C.c_int), ("yPer", C.c_int), ("zPer", C.c_int),
+        ("xGrid", C.c_int), ("yGrid", C.c_int), ("zGrid", C.c_int),
+        ("betaX", C.c_double), ("betaY", C.c_double), ("betaZ", C.c_double),
+        ("Lx", C.c_double), ("Ly", C.c_double), ("Lz", C.c_double),
+        ("vcDepth", C.c_int), ("vcCount", C.c_int), ("preSmooth", C.c_int),
+        ("postSmooth", C.c_int), ("gsSmooth", C.c_int), ("resType", C.c_int),
+        ("mgTolerance", C.c_double),
+        ("wall_null", C.c_int),
+    ]
+
+
+def build(fast=False):
+    """Compile the oracle with gcc (seconds).  Building the checker is not using it."""
+    target = "fast" if fast else "all"
+    subprocess.run(["make", "-s", "-C", _HERE, target], check=True)
+
+
+def _load(fast=False):
+    key = "fast" if fast else "strict"
+    if key in _LIBS:
+        return _LIBS[key]
+    name = "libmgoracle_fast.so" if fast else "libmgoracle.so"
+    path = os.path.join(_HERE, "_build", name)
+    src = os.path.join(_HERE, "mg_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        build(fast)
+    lib = C.CDLL(path)
+    vp, ip, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)
+    lib.mgo_create.restype = vp
+    lib.mgo_create.argtypes = [C.POINTER(MgoParams)]
+    lib.mgo_destroy.argtypes = [vp]
+    lib.mgo_nranks.argtypes = [vp]
+    lib.mgo_level_dims.argtypes = [vp, C.c_int, ip, ip]
+    lib.mgo_rank_info.argtypes = [vp, C.c_int, ip]
+    lib.mgo_metric.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
+    lib.mgo_coef.restype = C.c_double
+    lib.mgo_coef.argtypes = [vp, C.c_int, C.c_int]
+    lib.mgo_grid_spacing.argtypes = [vp, dp]
+    lib.mgo_staggr_coords.argtypes = [vp, C.c_int, C.c_int, dp]
+    lib.mgo_wall.argtypes = [vp, C.c_int, C.c_int, dp]
+    lib.mgo_max_count.argtypes = [vp]
+    lib.mgo_array.restype = dp
+    lib.mgo_array.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.mgo_set_level.argtypes = [vp, C.c_int]
+    lib.mgo_get_level.argtypes = [vp]
+    lib.mgo_set_zero_bc.argtypes = [vp, C.c_int]
+    lib.mgo_update_pads.argtypes = [vp, C.c_int]
+    for f in ("mgo_impose_bc", "mgo_compute_residual", "mgo_coarsen", "mgo_prolong", "mgo_vcycle", "mgo_lup_reset"):
+        getattr(lib, f).argtypes = [vp]
+    lib.mgo_smooth.argtypes = [vp, C.c_int]
+    lib.mgo_solve_coarsest.argtypes = [vp]
+    lib.mgo_compute_error.restype = C.c_double
+    lib.mgo_compute_error.argtypes = [vp, C.c_int]
+    lib.mgo_mg_solve.argtypes = [vp, C.POINTER(dp), C.POINTER(dp), dp, ip, dp]
+    lib.mgo_test_prolong.restype = C.c_double
+    lib.mgo_test_prolong.argtypes = [vp]
+    lib.mgo_lup_count.restype = C.c_double
+    lib.mgo_lup_count.argtypes = [vp]
+    _LIBS[key] = lib
+    return lib
+
+
+DEFAULTS = dict(dim=3, test_poisson=0, xInd=5, yInd=5, zInd=5, npX=1, npY=1, xPer=0, yPer=0, zPer=0,
+                xGrid=0, yGrid=0, zGrid=0, betaX=1.0, betaY=1.0, betaZ=1.0, Lx=1.0, Ly=1.0, Lz=1.0,
+                vcDepth=3, vcCount=10, preSmooth=2, postSmooth=2, gsSmooth=0, resType=2,
+                mgTolerance=1.0e-6, wall_null=1)
+
+
+class Oracle:
+    """All npX*npY ranks of the reference solver, emulated in one process."""
+
+    def __init__(self, fast=False, **kw):
+        cfg = dict(DEFAULTS)
+        cfg.update(kw)
+        if cfg["dim"] == 2:
+            cfg["yInd"] = 0
+            cfg["npY"] = 1
+        self.cfg = cfg
+        self.lib = _load(fast)
+        self.params = MgoParams(**cfg)
+        self.h = self.lib.mgo_create(C.byref(self.params))
+        self.nranks = self.lib.mgo_nranks(self.h)
+        self.depth = cfg["vcDepth"]
+
+    def close(self):
+        if self.h:
+            self.lib.mgo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- geometry ------------------------------------------------------------------------
+    def level_dims(self, level):
+        n = (C.c_int * 3)()
+        F = (C.c_int * 3)()
+        self.lib.mgo_level_dims(self.h, level, n, F)
+        return tuple(n), tuple(F)
+
+    def rank_info(self, rank):
+        out = (C.c_int * 6)()
+        self.lib.mgo_rank_info(self.h, rank, out)
+        return dict(xRank=out[0], yRank=out[1], faceRanks=[out[2], out[3], out[4], out[5]])
+
+    def metric(self, rank, level, which):
+        _, F = self.level_dims(level)
+        out = np.zeros(F[which // 2], dtype=np.float64)
+        self.lib.mgo_metric(self.h, rank, level, which, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def coef(self, level, which):
+        return self.lib.mgo_coef(self.h, level, which)
+
+    def spacing(self):
+        out = (C.c_double * 3)()
+        self.lib.mgo_grid_spacing(self.h, out)
+        return tuple(out)
+
+    def staggr(self, rank, d):
+        _, F = self.level_dims(0)
+        out = np.zeros(F[d], dtype=np.float64)
+        self.lib.mgo_staggr_coords(self.h, rank, d, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def wall(self, rank, which):
+        _, F = self.level_dims(0)
+        if self.cfg["dim"] == 3:
+            shape = [(F[1], F[2]), (F[0], F[2]), (F[0], F[1])][which]
+        else:
+            shape = [(F[2],), (0,), (F[0],)][which]
+        out = np.zeros(shape, dtype=np.float64)
+        if out.size:
+            self.lib.mgo_wall(self.h, rank, which, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    @property
+    def max_count(self):
+        return self.lib.mgo_max_count(self.h)
+
+    # -- level arrays (numpy views onto the oracle's memory) ---------------------------------
+    def array(self, rank, level, which):
+        _, F = self.level_dims(level)
+        ptr = self.lib.mgo_array(self.h, rank, level, which)
+        return np.ctypeslib.as_array(ptr, shape=F)
+
+    # -- operators ---------------------------------------------------------------------------
+    def set_level(self, v):
+        self.lib.mgo_set_level(self.h, v)
+
+    def get_level(self):
+        return self.lib.mgo_get_level(self.h)
+
+    def set_zero_bc(self, z):
+        self.lib.mgo_set_zero_bc(self.h, int(z))
+
+    def update_pads(self, which):
+        self.lib.mgo_update_pads(self.h, which)
+
+    def impose_bc(self):
+        self.lib.mgo_impose_bc(self.h)
+
+    def smooth(self, count):
+        self.lib.mgo_smooth(self.h, count)
+
+    def compute_residual(self):
+        self.lib.mgo_compute_residual(self.h)
+
+    def coarsen(self):
+        self.lib.mgo_coarsen(self.h)
+
+    def prolong(self):
+        self.lib.mgo_prolong(self.h)
+
+    def solve_coarsest(self):
+        return self.lib.mgo_solve_coarsest(self.h)
+
+    def compute_error(self, norm):
+        return self.lib.mgo_compute_error(self.h, norm)
+
+    def vcycle(self):
+        self.lib.mgo_vcycle(self.h)
+
+    def test_prolong(self):
+        return self.lib.mgo_test_prolong(self.h)
+
+    def lups(self):
+        return self.lib.mgo_lup_count(self.h)
+
+    def lup_reset(self):
+        self.lib.mgo_lup_reset(self.h)
+
+    def mg_solve(self, p_list, rhs_list):
+        """poisson::mgSolve.  p_list[r] (modified in place) and rhs_list[r]: padded level-0 arrays.
+        Returns dict(cycles, residuals, coarse_iters, max_dev)."""
+        nr = self.nranks
+        dp = C.POINTER(C.c_double)
+        for a in list(p_list) + list(rhs_list):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        P = (dp * nr)(*[a.ctypes.data_as(dp) for a in p_list])
+        R = (dp * nr)(*[a.ctypes.data_as(dp) for a in rhs_list])
+        vc = self.cfg["vcCount"]
+        hist = np.zeros(vc, dtype=np.float64)
+        iters = np.zeros(vc, dtype=np.int32)
+        dev = C.c_double(0.0)
+        cycles = self.lib.mgo_mg_solve(self.h, P, R, hist.ctypes.data_as(dp),
+                                       iters.ctypes.data_as(C.POINTER(C.c_int)), C.byref(dev))
+        return dict(cycles=cycles, residuals=hist[:cycles].copy(), coarse_iters=iters[:cycles].copy(),
+                    max_dev=dev.value)
