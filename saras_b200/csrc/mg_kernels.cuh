@@ -1,0 +1,697 @@
+/*
+ * mg_kernels.cuh -- hand-written sm_100a fp64 kernels of the multigrid pressure-Poisson solver.
+ *
+ * Every kernel reproduces the arithmetic of one loop nest of SARAS's lib/poisson (cited per kernel,
+ * "d3:N" = lib/poisson/poisson_d3.cc line N, "d2:N" = poisson_d2.cc, "p:N" = poisson.cc) operand for
+ * operand: this translation unit is compiled with -fmad=false, every division stays an IEEE division,
+ * and the association of every sum is the one the reference source spells out.  The path is an
+ * HBM-bound 7-point stencil: no tensor cores; the work is coalescing (z is the unit-stride axis and
+ * each thread owns an aligned pair of z points -> 128-bit loads/stores), register-blocked marching
+ * along x (three x-planes of the thread's column live in registers, so every pressure value is
+ * fetched from DRAM once per sweep) and keeping enough loads in flight.
+ *
+ * Device layout of a level array (private to the library): padded extents F = n + 2 with index base
+ * -1 as in the reference, z rows padded to `pitch` doubles with MG_LEAD leading slack doubles so that
+ * core point k = 0 of every row sits on a 32-byte sector boundary:
+ *     off(i,j,k) = (i+1)*plane + (j+1)*pitch + (k + 1 + MG_LEAD),  plane = F_y*pitch,  pitch % 4 == 0.
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+#define MG_LEAD 3
+
+struct LevelView {
+    int nx, ny, nz;         /* core points (xEnd+1, yEnd+1, zEnd+1) */
+    int Fx, Fy, Fz;         /* padded extents */
+    int pitch;              /* doubles per z row */
+    long long plane;        /* doubles per x plane = Fy*pitch */
+    /* metric arrays, pointers shifted so that [i] is index i (valid for -1..n) */
+    const double *xixx, *xix2, *etyy, *ety2, *ztzz, *ztz2;
+    double hx, hy, hz, hx2, hz2, hzhx, hxhy, hyhz, hxhyhz;
+};
+
+__host__ __device__ __forceinline__ long long mg_at(const LevelView &L, int i, int j, int k) {
+    return (long long)(i + 1) * L.plane + (long long)(j + 1) * L.pitch + (long long)(k + 1 + MG_LEAD);
+}
+
+/* face-operation modes (imposeBC d3:575-668, updatePads self-neighbour d3:671-686, pad zeroing d3:91) */
+enum { FACE_NONE = 0, FACE_MIRROR = 1, FACE_NEG_MIRROR = 2, FACE_WALL = 3, FACE_PERIODIC = 4, FACE_ZERO = 5 };
+
+/* ------------------------------------------------------------------------------------------------ */
+/* point formulas                                                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* d3:140-147 / 156-163 / 201-208.  c?2 = h??*metric2, c?1 = h??*metric1 are the leading products of each
+ * term (left-associated in the source, so forming them first is exact); den = 4.0*((cx2+cy2)+cz2). */
+__device__ __forceinline__ double relax3(double pE, double pW, double pN, double pS, double pT, double pB, double rhs,
+                                         double cx2, double cx1, double hx, double cy2, double cy1, double hy,
+                                         double cz2, double cz1, double hz, double two_hxhyhz, double den) {
+    double t = cx2 * (pE + pW) * 2.0;
+    t = t + cx1 * (pE - pW) * hx;
+    t = t + cy2 * (pN + pS) * 2.0;
+    t = t + cy1 * (pN - pS) * hy;
+    t = t + cz2 * (pT + pB) * 2.0;
+    t = t + cz1 * (pT - pB) * hz;
+    t = t - two_hxhyhz * rhs;
+    return t / den;
+}
+
+/* d2:121-126 / 133-138 / 160-165;  den = 4.0*(cx2 + cz2) */
+__device__ __forceinline__ double relax2(double pE, double pW, double pT, double pB, double rhs,
+                                         double cx2, double cx1, double hx, double cz2, double cz1, double hz,
+                                         double two_hzhx, double den) {
+    double t = cx2 * (pE + pW) * 2.0;
+    t = t + cx1 * (pE - pW) * hx;
+    t = t + cz2 * (pT + pB) * 2.0;
+    t = t + cz1 * (pT - pB) * hz;
+    t = t - two_hzhx * rhs;
+    return t / den;
+}
+
+/* the Laplacian bracket of d3:100-105 / 219-224 / 411-416.  dxx = hx*hx, dx = 2.0*hx, ... */
+__device__ __forceinline__ double lap3(double pC, double pE, double pW, double pN, double pS, double pT, double pB,
+                                       double x2, double x1, double y2, double y1, double z2, double z1,
+                                       double dxx, double dx, double dyy, double dy, double dzz, double dz) {
+    double t = x2 * (pE - 2.0 * pC + pW) / dxx;
+    t = t + x1 * (pE - pW) / dx;
+    t = t + y2 * (pN - 2.0 * pC + pS) / dyy;
+    t = t + y1 * (pN - pS) / dy;
+    t = t + z2 * (pT - 2.0 * pC + pB) / dzz;
+    t = t + z1 * (pT - pB) / dz;
+    return t;
+}
+
+/* d2:98-101 / 174-177 (dxx = hx*hx) and d2:293-296 (dxx = hx2) */
+__device__ __forceinline__ double lap2(double pC, double pE, double pW, double pT, double pB,
+                                       double x2, double x1, double z2, double z1,
+                                       double dxx, double dx, double dzz, double dz) {
+    double t = x2 * (pE - 2.0 * pC + pW) / dxx;
+    t = t + x1 * (pE - pW) / dx;
+    t = t + z2 * (pT - 2.0 * pC + pB) / dzz;
+    t = t + z1 * (pT - pB) / dz;
+    return t;
+}
+
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Jacobi sweep (d3:153-166, d2:131-140) and residual (d3:96-108, d2:95-103): x-marching kernels      */
+/* Thread = one aligned z pair (k0, k0+1) of row j; marches i over [i0, i1).                          */
+/* Algorithmic traffic: 24 B per core point (read p, read rhs, write out).                            */
+/* ------------------------------------------------------------------------------------------------ */
+template <int DIM, int MODE /* 0 Jacobi, 1 residual */>
+__global__ void __launch_bounds__(256)
+k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, double *__restrict__ O, const LevelView L,
+                const int ichunk) {
+    const int k0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int j = (DIM == 3) ? (blockIdx.y * blockDim.y + threadIdx.y) : 0;
+    if (k0 >= L.nz || j >= L.ny) return;
+    const int i0 = blockIdx.z * ichunk;
+    const int i1 = min(i0 + ichunk, L.nx);
+    const bool has2 = (k0 + 1 < L.nz);
+    const long long plane = L.plane;
+    const int pitch = L.pitch;
+    const long long row = (long long)(j + 1) * pitch + (k0 + 1 + MG_LEAD);
+    const double *p = P + row;
+    const double *r = R + row;
+    double *o = O + row;
+
+    /* per-thread constants */
+    const double z2a = L.ztz2[k0], z2b = L.ztz2[k0 + 1], z1a = L.ztzz[k0], z1b = L.ztzz[k0 + 1];
+    double y2 = 0.0, y1 = 0.0;
+    if (DIM == 3) { y2 = L.ety2[j]; y1 = L.etyy[j]; }
+    const double hx = L.hx, hy = L.hy, hz = L.hz;
+
+    /* MODE 0 */
+    double cy2 = 0.0, cy1 = 0.0, cz2a, cz2b, cz1a, cz1b, two_h, kx;
+    if (DIM == 3) {
+        cy2 = L.hzhx * y2; cy1 = L.hzhx * y1;
+        cz2a = L.hxhy * z2a; cz2b = L.hxhy * z2b; cz1a = L.hxhy * z1a; cz1b = L.hxhy * z1b;
+        two_h = 2.0 * L.hxhyhz; kx = L.hyhz;
+    } else {
+        cz2a = L.hx2 * z2a; cz2b = L.hx2 * z2b; cz1a = L.hx2 * z1a; cz1b = L.hx2 * z1b;
+        two_h = 2.0 * L.hzhx; kx = L.hz2;
+    }
+    /* MODE 1 */
+    const double dxx = hx * hx, dx = 2.0 * hx, dyy = hy * hy, dy = 2.0 * hy, dzz = hz * hz, dz = 2.0 * hz;
+
+    double2 pW = ld2(p + (long long)i0 * plane);          /* plane i0-1 */
+    double2 pC = ld2(p + (long long)(i0 + 1) * plane);    /* plane i0   */
+    for (int i = i0; i < i1; ++i) {
+        const long long b = (long long)(i + 1) * plane;
+        const double2 pE = ld2(p + b + plane);
+        const double2 rr = ld2(r + b);
+        const double pBa = p[b - 1];        /* (i, j, k0-1) */
+        const double pTb = p[b + 2];        /* (i, j, k0+2) */
+        double2 pS = make_double2(0.0, 0.0), pN = make_double2(0.0, 0.0);
+        if (DIM == 3) { pS = ld2(p + b - pitch); pN = ld2(p + b + pitch); }
+        const double x2 = L.xix2[i], x1 = L.xixx[i];
+        double2 out;
+        if (MODE == 0) {
+            const double cx2 = kx * x2, cx1 = kx * x1;
+            if (DIM == 3) {
+                const double s = cx2 + cy2;
+                out.x = relax3(pE.x, pW.x, pN.x, pS.x, pC.y, pBa, rr.x, cx2, cx1, hx, cy2, cy1, hy, cz2a, cz1a, hz, two_h, 4.0 * (s + cz2a));
+                out.y = relax3(pE.y, pW.y, pN.y, pS.y, pTb, pC.x, rr.y, cx2, cx1, hx, cy2, cy1, hy, cz2b, cz1b, hz, two_h, 4.0 * (s + cz2b));
+            } else {
+                out.x = relax2(pE.x, pW.x, pC.y, pBa, rr.x, cx2, cx1, hx, cz2a, cz1a, hz, two_h, 4.0 * (cx2 + cz2a));
+                out.y = relax2(pE.y, pW.y, pTb, pC.x, rr.y, cx2, cx1, hx, cz2b, cz1b, hz, two_h, 4.0 * (cx2 + cz2b));
+            }
+        } else {
+            if (DIM == 3) {
+                out.x = rr.x - lap3(pC.x, pE.x, pW.x, pN.x, pS.x, pC.y, pBa, x2, x1, y2, y1, z2a, z1a, dxx, dx, dyy, dy, dzz, dz);
+                out.y = rr.y - lap3(pC.y, pE.y, pW.y, pN.y, pS.y, pTb, pC.x, x2, x1, y2, y1, z2b, z1b, dxx, dx, dyy, dy, dzz, dz);
+            } else {
+                out.x = rr.x - lap2(pC.x, pE.x, pW.x, pC.y, pBa, x2, x1, z2a, z1a, dxx, dx, dzz, dz);
+                out.y = rr.y - lap2(pC.y, pE.y, pW.y, pTb, pC.x, x2, x1, z2b, z1b, dxx, dx, dzz, dz);
+            }
+        }
+        if (has2) st2(o + b, out); else o[b] = out.x;
+        pW = pC; pC = pE;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* computeError (d3:408-430, d2:291-309): |L p - rhs| reduced to max / sum of squares; no store.       */
+/* partial layout: part[0*nb + b] = num, part[1*nb + b] = den(sum rhs^2), b = linear block id.         */
+/* ------------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+/* deterministic block reduction (fixed shuffle tree); result valid in thread 0 */
+template <bool IS_MAX>
+__device__ __forceinline__ double block_reduce(double v, double *sm /* >= 32 doubles */) {
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int nthr = blockDim.x * blockDim.y;
+    const int lane = tid & 31, w = tid >> 5;
+    v = IS_MAX ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    const int nw = (nthr + 31) >> 5;
+    if (w == 0) {
+        v = (lane < nw) ? sm[lane] : (IS_MAX ? -1.0e300 : 0.0);
+        v = IS_MAX ? warp_max(v) : warp_sum(v);
+    }
+    return v;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_error_march(const double *__restrict__ P, const double *__restrict__ R, const LevelView L, const int ichunk,
+              const int norm_order, double hx_c, double hy_c, double hz_c, double *__restrict__ part, const int nblocks) {
+    __shared__ double sm[32];
+    const int k0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int j = (DIM == 3) ? (blockIdx.y * blockDim.y + threadIdx.y) : 0;
+    const bool active = !(k0 >= L.nz || j >= L.ny);
+    double num = 0.0, den = 0.0;
+    if (active) {
+        const int i0 = blockIdx.z * ichunk;
+        const int i1 = min(i0 + ichunk, L.nx);
+        const bool has2 = (k0 + 1 < L.nz);
+        const long long plane = L.plane;
+        const int pitch = L.pitch;
+        const long long row = (long long)(j + 1) * pitch + (k0 + 1 + MG_LEAD);
+        const double *p = P + row;
+        const double *r = R + row;
+        const double z2a = L.ztz2[k0], z2b = L.ztz2[k0 + 1], z1a = L.ztzz[k0], z1b = L.ztzz[k0 + 1];
+        double y2 = 0.0, y1 = 0.0;
+        if (DIM == 3) { y2 = L.ety2[j]; y1 = L.etyy[j]; }
+        /* d3:411-416 divides by hx(vLevel)*hx(vLevel); d2:293-296 by hx2(0), hz2(0) */
+        const double dxx = (DIM == 3) ? hx_c * hx_c : L.hx2, dx = 2.0 * hx_c;
+        const double dyy = hy_c * hy_c, dy = 2.0 * hy_c;
+        const double dzz = (DIM == 3) ? hz_c * hz_c : L.hz2, dz = 2.0 * hz_c;
+        double2 pW = ld2(p + (long long)i0 * plane);
+        double2 pC = ld2(p + (long long)(i0 + 1) * plane);
+        for (int i = i0; i < i1; ++i) {
+            const long long b = (long long)(i + 1) * plane;
+            const double2 pE = ld2(p + b + plane);
+            const double2 rr = ld2(r + b);
+            const double pBa = p[b - 1];
+            const double pTb = p[b + 2];
+            double2 pS = make_double2(0.0, 0.0), pN = make_double2(0.0, 0.0);
+            if (DIM == 3) { pS = ld2(p + b - pitch); pN = ld2(p + b + pitch); }
+            const double x2 = L.xix2[i], x1 = L.xixx[i];
+            double ta, tb;
+            if (DIM == 3) {
+                ta = fabs(lap3(pC.x, pE.x, pW.x, pN.x, pS.x, pC.y, pBa, x2, x1, y2, y1, z2a, z1a, dxx, dx, dyy, dy, dzz, dz) - rr.x);
+                tb = fabs(lap3(pC.y, pE.y, pW.y, pN.y, pS.y, pTb, pC.x, x2, x1, y2, y1, z2b, z1b, dxx, dx, dyy, dy, dzz, dz) - rr.y);
+            } else {
+                ta = fabs(lap2(pC.x, pE.x, pW.x, pC.y, pBa, x2, x1, z2a, z1a, dxx, dx, dzz, dz) - rr.x);
+                tb = fabs(lap2(pC.y, pE.y, pW.y, pTb, pC.x, x2, x1, z2b, z1b, dxx, dx, dzz, dz) - rr.y);
+            }
+            if (norm_order == 1) {
+                num = fmax(num, ta);
+                if (has2) num = fmax(num, tb);
+            } else {
+                num += ta * ta; den += rr.x * rr.x;
+                if (has2) { num += tb * tb; den += rr.y * rr.y; }
+            }
+            pW = pC; pC = pE;
+        }
+    }
+    const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    double n2 = (norm_order == 1) ? block_reduce<true>(num, sm) : block_reduce<false>(num, sm);
+    double d2 = block_reduce<false>(den, sm);
+    if (threadIdx.x == 0 && threadIdx.y == 0) { part[bid] = n2; part[nblocks + bid] = d2; }
+}
+
+/* final stage: one block reduces `n` partials of `nq` quantities in a fixed order.
+ * is_max bit q set -> quantity q is a max-reduction.  out[q] receives the result. */
+__global__ void __launch_bounds__(1024) k_reduce_final(const double *__restrict__ part, const int n, const int nq,
+                                                      const unsigned is_max, double *__restrict__ out) {
+    __shared__ double sm[32];
+    for (int q = 0; q < nq; ++q) {
+        const bool mx = (is_max >> q) & 1u;
+        double v = mx ? -1.0e300 : 0.0;
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+            const double x = part[(long long)q * n + idx];
+            v = mx ? fmax(v, x) : v + x;
+        }
+        v = mx ? block_reduce<true>(v, sm) : block_reduce<false>(v, sm);
+        if (threadIdx.x == 0) out[q] = v;
+        __syncthreads();
+    }
+}
+
+/* reductions over the WHOLE padded array (blitz::mean p:122; blitz::max(fabs()) d3:437): one block per (i,j) row group */
+template <int WHAT /* 0 sum, 1 absmax */>
+__global__ void __launch_bounds__(256) k_reduce_padded(const double *__restrict__ A, const LevelView L, double *__restrict__ part) {
+    __shared__ double sm[32];
+    const long long rows = (long long)L.Fx * L.Fy;
+    double v = (WHAT == 1) ? -1.0e300 : 0.0;
+    for (long long rrow = blockIdx.x; rrow < rows; rrow += gridDim.x) {
+        const double *a = A + rrow * L.pitch + MG_LEAD;
+        for (int k = threadIdx.x; k < L.Fz; k += blockDim.x) {
+            const double x = a[k];
+            v = (WHAT == 1) ? fmax(v, fabs(x)) : v + x;
+        }
+    }
+    v = (WHAT == 1) ? block_reduce<true>(v, sm) : block_reduce<false>(v, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+/* residualData(0) -= globalAvg over the whole padded array (p:128) */
+__global__ void __launch_bounds__(256) k_sub_scalar_padded(double *__restrict__ A, const LevelView L, const double v) {
+    const long long rows = (long long)L.Fx * L.Fy;
+    for (long long rrow = blockIdx.x; rrow < rows; rrow += gridDim.x) {
+        double *a = A + rrow * L.pitch + MG_LEAD;
+        for (int k = threadIdx.x; k < L.Fz; k += blockDim.x) a[k] = a[k] - v;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* face operations: physical BCs (imposeBC d3:578-667, d2:406-463), periodic self-neighbour halos      */
+/* (updatePads with faceRanks == own rank, d3:675-685) and pad zeroing (d3:91).  Strided-loop form so   */
+/* the same code runs grid-wide and inside the single-CTA coarse solver.                               */
+/* ------------------------------------------------------------------------------------------------ */
+template <int DIR>
+__device__ __forceinline__ void face_op(double *A, const LevelView &L, const int lo_mode, const int hi_mode,
+                                        const double *wall, const bool planar, const long long tid, const long long nthr) {
+    const int jlo = planar ? 0 : -1;
+    const int nj = planar ? 1 : L.Fy;
+    if (DIR == 0) {
+        const int xE = L.nx - 1;
+        const long long cnt = (long long)nj * L.Fz;
+        for (long long q = tid; q < cnt; q += nthr) {
+            const int j = jlo + (int)(q / L.Fz), k = (int)(q % L.Fz) - 1;
+            const double w = (lo_mode == FACE_WALL || hi_mode == FACE_WALL) ? (planar ? wall[k + 1] : wall[(long long)(j + 1) * L.Fz + (k + 1)]) : 0.0;
+            if (lo_mode != FACE_NONE) {
+                double v;
+                if (lo_mode == FACE_MIRROR) v = A[mg_at(L, 1, j, k)];
+                else if (lo_mode == FACE_NEG_MIRROR) v = -A[mg_at(L, 1, j, k)];
+                else if (lo_mode == FACE_WALL) v = w;
+                else if (lo_mode == FACE_PERIODIC) v = A[mg_at(L, xE - 1, j, k)];
+                else v = 0.0;
+                A[mg_at(L, -1, j, k)] = v;
+            }
+            if (hi_mode != FACE_NONE) {
+                double v;
+                if (hi_mode == FACE_MIRROR) v = A[mg_at(L, xE - 1, j, k)];
+                else if (hi_mode == FACE_NEG_MIRROR) v = -A[mg_at(L, xE - 1, j, k)];
+                else if (hi_mode == FACE_WALL) v = w;
+                else if (hi_mode == FACE_PERIODIC) v = A[mg_at(L, 1, j, k)];
+                else v = 0.0;
+                A[mg_at(L, xE + 1, j, k)] = v;
+            }
+        }
+    } else if (DIR == 1) {
+        const int yE = L.ny - 1;
+        const long long cnt = (long long)L.Fx * L.Fz;
+        for (long long q = tid; q < cnt; q += nthr) {
+            const int i = (int)(q / L.Fz) - 1, k = (int)(q % L.Fz) - 1;
+            const double w = (lo_mode == FACE_WALL || hi_mode == FACE_WALL) ? wall[(long long)(i + 1) * L.Fz + (k + 1)] : 0.0;
+            if (lo_mode != FACE_NONE) {
+                double v;
+                if (lo_mode == FACE_MIRROR) v = A[mg_at(L, i, 1, k)];
+                else if (lo_mode == FACE_NEG_MIRROR) v = -A[mg_at(L, i, 1, k)];
+                else if (lo_mode == FACE_WALL) v = w;
+                else if (lo_mode == FACE_PERIODIC) v = A[mg_at(L, i, yE - 1, k)];
+                else v = 0.0;
+                A[mg_at(L, i, -1, k)] = v;
+            }
+            if (hi_mode != FACE_NONE) {
+                double v;
+                if (hi_mode == FACE_MIRROR) v = A[mg_at(L, i, yE - 1, k)];
+                else if (hi_mode == FACE_NEG_MIRROR) v = -A[mg_at(L, i, yE - 1, k)];
+                else if (hi_mode == FACE_WALL) v = w;
+                else if (hi_mode == FACE_PERIODIC) v = A[mg_at(L, i, 1, k)];
+                else v = 0.0;
+                A[mg_at(L, i, yE + 1, k)] = v;
+            }
+        }
+    } else {
+        const int zE = L.nz - 1;
+        const long long cnt = (long long)L.Fx * nj;
+        for (long long q = tid; q < cnt; q += nthr) {
+            const int i = (int)(q / nj) - 1, j = jlo + (int)(q % nj);
+            const double w = (lo_mode == FACE_WALL || hi_mode == FACE_WALL) ? (planar ? wall[i + 1] : wall[(long long)(i + 1) * L.Fy + (j + 1)]) : 0.0;
+            if (lo_mode != FACE_NONE) {
+                double v;
+                if (lo_mode == FACE_MIRROR) v = A[mg_at(L, i, j, 1)];
+                else if (lo_mode == FACE_NEG_MIRROR) v = -A[mg_at(L, i, j, 1)];
+                else if (lo_mode == FACE_WALL) v = w;
+                else if (lo_mode == FACE_PERIODIC) v = A[mg_at(L, i, j, zE - 1)];
+                else v = 0.0;
+                A[mg_at(L, i, j, -1)] = v;
+            }
+            if (hi_mode != FACE_NONE) {
+                double v;
+                if (hi_mode == FACE_MIRROR) v = A[mg_at(L, i, j, zE - 1)];
+                else if (hi_mode == FACE_NEG_MIRROR) v = -A[mg_at(L, i, j, zE - 1)];
+                else if (hi_mode == FACE_WALL) v = w;
+                else if (hi_mode == FACE_PERIODIC) v = A[mg_at(L, i, j, 1)];
+                else v = 0.0;
+                A[mg_at(L, i, j, zE + 1)] = v;
+            }
+        }
+    }
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(256) k_face(double *A, const LevelView L, const int lo_mode, const int hi_mode,
+                                              const double *wall, const int planar) {
+    face_op<DIR>(A, L, lo_mode, hi_mode, wall, planar != 0, (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                 (long long)gridDim.x * blockDim.x);
+}
+
+/* y-row pack/unpack for the inter-GPU halo (MPI_Type_vector of d3:492-497): row j of every x plane <-> contiguous buffer */
+__global__ void __launch_bounds__(256) k_pack_y(const double *__restrict__ A, const LevelView L, const int j, double *__restrict__ buf) {
+    const long long cnt = (long long)L.Fx * L.Fz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q / L.Fz) - 1, k = (int)(q % L.Fz) - 1;
+        buf[q] = A[mg_at(L, i, j, k)];
+    }
+}
+__global__ void __launch_bounds__(256) k_unpack_y(double *__restrict__ A, const LevelView L, const int j, const double *__restrict__ buf) {
+    const long long cnt = (long long)L.Fx * L.Fz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q / L.Fz) - 1, k = (int)(q % L.Fz) - 1;
+        A[mg_at(L, i, j, k)] = buf[q];
+    }
+}
+/* x-plane pack/unpack (MPI_Type_contiguous of d3:486-489; 2-D: row j=0 only, d2:353-356) into a compact buffer */
+__global__ void __launch_bounds__(256) k_pack_x(const double *__restrict__ A, const LevelView L, const int i, const int planar, double *__restrict__ buf) {
+    const int nj = planar ? 1 : L.Fy;
+    const long long cnt = (long long)nj * L.Fz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
+        const int j = (planar ? 0 : -1) + (int)(q / L.Fz), k = (int)(q % L.Fz) - 1;
+        buf[q] = A[mg_at(L, i, j, k)];
+    }
+}
+__global__ void __launch_bounds__(256) k_unpack_x(double *__restrict__ A, const LevelView L, const int i, const int planar, const double *__restrict__ buf) {
+    const int nj = planar ? 1 : L.Fy;
+    const long long cnt = (long long)nj * L.Fz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
+        const int j = (planar ? 0 : -1) + (int)(q / L.Fz), k = (int)(q % L.Fz) - 1;
+        A[mg_at(L, i, j, k)] = buf[q];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* full-weighting restriction (d3:270-297, d2:222-235): thread per coarse point, sums in source order */
+/* ------------------------------------------------------------------------------------------------ */
+template <int DIM>
+__global__ void __launch_bounds__(256) k_coarsen(const double *__restrict__ T, const LevelView Lf, double *__restrict__ Rc, const LevelView Lc) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (DIM == 3) ? blockIdx.y * blockDim.y + threadIdx.y : 0;
+    const int i = blockIdx.z;
+    if (k >= Lc.nz || j >= Lc.ny || i >= Lc.nx) return;
+    const int i2 = i * 2, j2 = j * 2, k2 = k * 2;
+#define TF(a, b, c) T[mg_at(Lf, (a), (b), (c))]
+    if (DIM == 3) {
+        const double facePoints = (TF(i2 + 1, j2, k2) + TF(i2 - 1, j2, k2) +
+                                   TF(i2, j2 + 1, k2) + TF(i2, j2 - 1, k2) +
+                                   TF(i2, j2, k2 + 1) + TF(i2, j2, k2 - 1)) * 0.0625;
+        const double edgePoints = (TF(i2 + 1, j2 + 1, k2) + TF(i2 + 1, j2 - 1, k2) +
+                                   TF(i2 - 1, j2 - 1, k2) + TF(i2 - 1, j2 + 1, k2) +
+                                   TF(i2, j2 + 1, k2 + 1) + TF(i2, j2 - 1, k2 + 1) +
+                                   TF(i2, j2 - 1, k2 - 1) + TF(i2, j2 + 1, k2 - 1) +
+                                   TF(i2 + 1, j2, k2 + 1) + TF(i2 + 1, j2, k2 - 1) +
+                                   TF(i2 - 1, j2, k2 - 1) + TF(i2 - 1, j2, k2 + 1)) * 0.03125;
+        const double vertPoints = (TF(i2 + 1, j2 + 1, k2 + 1) +
+                                   TF(i2 + 1, j2 + 1, k2 - 1) +
+                                   TF(i2 + 1, j2 - 1, k2 + 1) +
+                                   TF(i2 - 1, j2 + 1, k2 + 1) +
+                                   TF(i2 + 1, j2 - 1, k2 - 1) +
+                                   TF(i2 - 1, j2 + 1, k2 - 1) +
+                                   TF(i2 - 1, j2 - 1, k2 + 1) +
+                                   TF(i2 - 1, j2 - 1, k2 - 1)) * 0.015625;
+        Rc[mg_at(Lc, i, j, k)] = facePoints + edgePoints + vertPoints + TF(i2, j2, k2) * 0.125;
+    } else {
+        const double facePoints = (TF(i2 + 1, 0, k2) + TF(i2 - 1, 0, k2) +
+                                   TF(i2, 0, k2 + 1) + TF(i2, 0, k2 - 1)) * 0.125;
+        const double vertPoints = (TF(i2 + 1, 0, k2 + 1) +
+                                   TF(i2 + 1, 0, k2 - 1) +
+                                   TF(i2 - 1, 0, k2 + 1) +
+                                   TF(i2 - 1, 0, k2 - 1)) * 0.0625;
+        Rc[mg_at(Lc, i, 0, k)] = facePoints + vertPoints + TF(i2, 0, k2) * 0.25;
+    }
+#undef TF
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* prolongation fused with "pressureData += smoothedPres" (d3:310-365 + p:271; d2:248-270).            */
+/* The fine array still holds the pre-coarsening iterate (it IS smoothedPres), so                      */
+/*    fine[idx] = interp + fine[idx]   ( = (0 + interp) + smoothedPres, addition commutes exactly ).   */
+/* Algorithmic traffic 17 B per fine point.                                                           */
+/* ------------------------------------------------------------------------------------------------ */
+template <int DIM>
+__global__ void __launch_bounds__(256) k_prolong_add(const double *__restrict__ C, const LevelView Lc, double *__restrict__ Pf, const LevelView Lf) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (DIM == 3) ? blockIdx.y * blockDim.y + threadIdx.y : 0;
+    const int i = blockIdx.z;
+    if (k >= Lf.nz || j >= Lf.ny || i >= Lf.nx) return;
+    const int i2 = i / 2, j2 = j / 2, k2 = k / 2;
+    const bool oi = i & 1, oj = (DIM == 3) ? (j & 1) : false, ok = k & 1;
+#define PC(a, b, c) C[mg_at(Lc, (a), (b), (c))]
+    double v;
+    if (DIM == 3) {
+        if (oi) {
+            if (oj) {
+                if (ok) v = (PC(i2, j2, k2) +
+                             PC(i2 + 1, j2, k2) + PC(i2, j2 + 1, k2) + PC(i2, j2, k2 + 1) +
+                             PC(i2 + 1, j2 + 1, k2) + PC(i2 + 1, j2, k2 + 1) + PC(i2, j2 + 1, k2 + 1) +
+                             PC(i2 + 1, j2 + 1, k2 + 1)) / 8.0;
+                else    v = (PC(i2, j2, k2) + PC(i2, j2 + 1, k2) + PC(i2 + 1, j2, k2) + PC(i2 + 1, j2 + 1, k2)) / 4.0;
+            } else {
+                if (ok) v = (PC(i2, j2, k2) + PC(i2, j2, k2 + 1) + PC(i2 + 1, j2, k2) + PC(i2 + 1, j2, k2 + 1)) / 4.0;
+                else    v = (PC(i2, j2, k2) + PC(i2 + 1, j2, k2)) / 2.0;
+            }
+        } else {
+            if (oj) {
+                if (ok) v = (PC(i2, j2, k2) + PC(i2, j2, k2 + 1) + PC(i2, j2 + 1, k2) + PC(i2, j2 + 1, k2 + 1)) / 4.0;
+                else    v = (PC(i2, j2, k2) + PC(i2, j2 + 1, k2)) / 2.0;
+            } else {
+                if (ok) v = (PC(i2, j2, k2) + PC(i2, j2, k2 + 1)) / 2.0;
+                else    v = PC(i2, j2, k2);
+            }
+        }
+    } else {
+        if (oi) {
+            if (ok) v = (PC(i2, 0, k2) + PC(i2, 0, k2 + 1) + PC(i2 + 1, 0, k2) + PC(i2 + 1, 0, k2 + 1)) / 4.0;
+            else    v = (PC(i2, 0, k2) + PC(i2 + 1, 0, k2)) / 2.0;
+        } else {
+            if (ok) v = (PC(i2, 0, k2) + PC(i2, 0, k2 + 1)) / 2.0;
+            else    v = PC(i2, 0, k2);
+        }
+    }
+#undef PC
+    const long long idx = mg_at(Lf, i, j, k);
+    Pf[idx] = v + Pf[idx];
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* exact lexicographic Gauss-Seidel as a hyperplane wavefront (d3:137-150, d2:119-128).                */
+/* Point (i,j,k) reads the NEW values of (i-1,j,k), (i,j-1,k), (i,j,k-1) and the OLD values of the +1   */
+/* neighbours; all points with i+j+k = h are mutually independent and see exactly the operands the      */
+/* sequential i->j->k loop would give them, so processing h = 0,1,2,... in order is bit-identical.      */
+/* ------------------------------------------------------------------------------------------------ */
+template <int DIM>
+__device__ __forceinline__ void gs_point(double *P, const double *R, const LevelView &L, const int i, const int j, const int k) {
+    const long long c = mg_at(L, i, j, k);
+    if (DIM == 3) {
+        const double cx2 = L.hyhz * L.xix2[i], cx1 = L.hyhz * L.xixx[i];
+        const double cy2 = L.hzhx * L.ety2[j], cy1 = L.hzhx * L.etyy[j];
+        const double cz2 = L.hxhy * L.ztz2[k], cz1 = L.hxhy * L.ztzz[k];
+        P[c] = relax3(P[c + L.plane], P[c - L.plane], P[c + L.pitch], P[c - L.pitch], P[c + 1], P[c - 1], R[c],
+                      cx2, cx1, L.hx, cy2, cy1, L.hy, cz2, cz1, L.hz, 2.0 * L.hxhyhz, 4.0 * (cx2 + cy2 + cz2));
+    } else {
+        const double cx2 = L.hz2 * L.xix2[i], cx1 = L.hz2 * L.xixx[i];
+        const double cz2 = L.hx2 * L.ztz2[k], cz1 = L.hx2 * L.ztzz[k];
+        P[c] = relax2(P[c + L.plane], P[c - L.plane], P[c + 1], P[c - 1], R[c],
+                      cx2, cx1, L.hx, cz2, cz1, L.hz, 2.0 * L.hzhx, 4.0 * (cx2 + cz2));
+    }
+}
+
+/* one hyperplane: threads over (j fast, i slow) for 3-D, over i for 2-D */
+template <int DIM>
+__global__ void __launch_bounds__(256) k_gs_plane(double *P, const double *__restrict__ R, const LevelView L, const int h, const int ilo) {
+    if (DIM == 3) {
+        const int j = blockIdx.x * blockDim.x + threadIdx.x;
+        const int i = ilo + blockIdx.y * blockDim.y + threadIdx.y;
+        const int k = h - i - j;
+        if (j >= L.ny || i >= L.nx || k < 0 || k >= L.nz) return;
+        gs_point<3>(P, R, L, i, j, k);
+    } else {
+        const int i = ilo + blockIdx.x * blockDim.x + threadIdx.x;
+        const int k = h - i;
+        if (i >= L.nx || k < 0 || k >= L.nz) return;
+        gs_point<2>(P, R, L, i, 0, k);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* residual max for the coarsest-level solve (d3:213-231, d2:169-183): max(|rhs - L p|, -1e-10)        */
+/* ------------------------------------------------------------------------------------------------ */
+template <int DIM>
+__device__ __forceinline__ double resid_abs_point(const double *P, const double *R, const LevelView &L, const int i, const int j, const int k) {
+    const long long c = mg_at(L, i, j, k);
+    if (DIM == 3) {
+        return fabs(R[c] - lap3(P[c], P[c + L.plane], P[c - L.plane], P[c + L.pitch], P[c - L.pitch], P[c + 1], P[c - 1],
+                                L.xix2[i], L.xixx[i], L.ety2[j], L.etyy[j], L.ztz2[k], L.ztzz[k],
+                                L.hx * L.hx, 2.0 * L.hx, L.hy * L.hy, 2.0 * L.hy, L.hz * L.hz, 2.0 * L.hz));
+    } else {
+        return fabs(R[c] - lap2(P[c], P[c + L.plane], P[c - L.plane], P[c + 1], P[c - 1],
+                                L.xix2[i], L.xixx[i], L.ztz2[k], L.ztzz[k],
+                                L.hx * L.hx, 2.0 * L.hx, L.hz * L.hz, 2.0 * L.hz));
+    }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_resid_max(const double *__restrict__ P, const double *__restrict__ R, const LevelView L, double *__restrict__ part) {
+    __shared__ double sm[32];
+    const long long cnt = (long long)L.nx * L.ny * L.nz;
+    double m = -1.0e-10;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(q % L.nz);
+        const int j = (int)((q / L.nz) % L.ny);
+        const int i = (int)(q / ((long long)L.nz * L.ny));
+        m = fmax(m, resid_abs_point<DIM>(P, R, L, i, j, k));
+    }
+    m = block_reduce<true>(m, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = m;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Coarsest-level solve, single rank: the whole `while(true)` of d3:190-247 / d2:150-199 in ONE CTA.   */
+/* imposeBC (self-neighbour pad copies x then y, then wall BCs x, y, z), exact GS wavefront, residual   */
+/* max and the convergence test all stay on the device; the iteration count is written to *iters_out.  */
+/* ------------------------------------------------------------------------------------------------ */
+struct BcPlan {
+    int pad_x_lo, pad_x_hi, pad_y_lo, pad_y_hi;   /* FACE_PERIODIC where the neighbour is this rank itself, else FACE_NONE */
+    int bc_x_lo, bc_x_hi, bc_y_lo, bc_y_hi, bc_z_lo, bc_z_hi;
+    const double *xwall, *ywall, *zwall;
+    int planar;
+};
+
+template <int DIM>
+__device__ void cta_impose_bc(double *P, const LevelView &L, const BcPlan &B) {
+    const long long tid = threadIdx.x, nthr = blockDim.x;
+    if (B.pad_x_lo | B.pad_x_hi) { face_op<0>(P, L, B.pad_x_lo, B.pad_x_hi, nullptr, B.planar, tid, nthr); __syncthreads(); }
+    if (DIM == 3 && (B.pad_y_lo | B.pad_y_hi)) { face_op<1>(P, L, B.pad_y_lo, B.pad_y_hi, nullptr, B.planar, tid, nthr); __syncthreads(); }
+    if (B.bc_x_lo | B.bc_x_hi) { face_op<0>(P, L, B.bc_x_lo, B.bc_x_hi, B.xwall, B.planar, tid, nthr); __syncthreads(); }
+    if (DIM == 3 && (B.bc_y_lo | B.bc_y_hi)) { face_op<1>(P, L, B.bc_y_lo, B.bc_y_hi, B.ywall, B.planar, tid, nthr); __syncthreads(); }
+    if (B.bc_z_lo | B.bc_z_hi) { face_op<2>(P, L, B.bc_z_lo, B.bc_z_hi, B.zwall, B.planar, tid, nthr); __syncthreads(); }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(1024) k_coarse_solve(double *P, const double *R, const LevelView L, const BcPlan B,
+                                                      const double tol, const int maxCount, int *iters_out) {
+    __shared__ double sm[32];
+    __shared__ double s_max;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int H = L.nx + L.ny + L.nz - 2;
+    const int nij = L.nx * L.ny;
+    const long long cnt = (long long)nij * L.nz;
+    int iter = 0;
+    while (true) {
+        cta_impose_bc<DIM>(P, L, B);
+        for (int h = 0; h < H; ++h) {
+            for (int q = tid; q < nij; q += nthr) {
+                const int i = q / L.ny, j = q % L.ny;
+                const int k = h - i - j;
+                if (k >= 0 && k < L.nz) gs_point<DIM>(P, R, L, i, j, k);
+            }
+            __syncthreads();
+        }
+        double m = -1.0e-10;
+        for (long long q = tid; q < cnt; q += nthr) {
+            const int k = (int)(q % L.nz);
+            const int j = (int)((q / L.nz) % L.ny);
+            const int i = (int)(q / ((long long)L.nz * L.ny));
+            m = fmax(m, resid_abs_point<DIM>(P, R, L, i, j, k));
+        }
+        m = block_reduce<true>(m, sm);
+        if (tid == 0) s_max = m;
+        __syncthreads();
+        const double gmax = s_max;
+        __syncthreads();
+        if (gmax < tol) break;
+        iter += 1;
+        if (iter > maxCount) break;
+    }
+    cta_impose_bc<DIM>(P, L, B);
+    if (tid == 0) *iters_out = iter;
+}
+
+/* misc */
+__global__ void __launch_bounds__(256) k_fill(double *__restrict__ A, const long long n, const double v) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) A[q] = v;
+}
+/* copy the CORE of src into dst (p:114-115); both level-0 pitched arrays */
+__global__ void __launch_bounds__(256) k_copy_core(const double *__restrict__ S, double *__restrict__ Dst, const LevelView L) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int i = blockIdx.z;
+    if (k >= L.nz) return;
+    const long long c = mg_at(L, i, j, k);
+    Dst[c] = S[c];
+}
+/* TEST_POISSON epilogue p:153-204: max |analytic - p| over the core */
+__global__ void __launch_bounds__(256) k_analytic_dev(const double *__restrict__ P, const LevelView L, const int dim,
+                                                      const int xoff, const int yoff, const int halfX, const int halfY,
+                                                      double *__restrict__ part) {
+    __shared__ double sm[32];
+    const long long cnt = (long long)L.nx * L.ny * L.nz;
+    const int ubz = L.nz - 1;
+    double m = -1.0e300;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(q % L.nz);
+        const int j = (int)((q / L.nz) % L.ny);
+        const int i = (int)(q / ((long long)L.nz * L.ny));
+        const double xDist = L.hx * (xoff + i - halfX);
+        const double yDist = L.hy * (yoff + j - halfY);
+        const double zDist = L.hz * (k - ubz / 2);
+        const double pa = (dim == 3) ? (xDist * xDist + yDist * yDist + zDist * zDist) / 6.0 : (xDist * xDist + zDist * zDist) / 4.0;
+        m = fmax(m, fabs(pa - P[mg_at(L, i, j, k)]));
+    }
+    m = block_reduce<true>(m, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = m;
+}

@@ -1,0 +1,1115 @@
+/*
+ * sarasmg.cu -- device-resident multigrid hierarchy, V-cycle driver and the extern "C" layer
+ * declared in include/sarasmg.h.  Control flow follows SARAS's lib/poisson/poisson.cc (mgSolve
+ * :100-205, vCycle :219-280) and poisson_d3.cc / poisson_d2.cc statement by statement; the
+ * arithmetic lives in mg_kernels.cuh.  There is no CPU fallback.
+ *
+ * Differences from the reference's data handling that do not change any result:
+ *   - smoothedPres (poisson.h:73) is not stored.  pressureData(l) is dead between p:252 and p:271
+ *     (it is zeroed by prolong() at d3:308 before being read again), so the device keeps the
+ *     pre-coarsening iterate in place and k_prolong_add adds the interpolated correction to it.
+ *   - tmpDataArray(l) = 0 (d3:91, d3:118) is reduced to zeroing its pads: the core is overwritten
+ *     before it is read, and in smooth() every pad plane is rewritten by imposeBC.
+ *   - swap(tmpDataArray, pressureData) (d3:168) swaps every level at once in the reference; all the
+ *     other levels are dead or re-initialised before use, so a per-level pointer swap is equivalent.
+ */
+#include "../../include/sarasmg.h"
+#include "mg_kernels.cuh"
+
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+
+static int set_err(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) return set_err("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+#define NC(call)                                                                                     \
+    do {                                                                                             \
+        ncclResult_t r_ = (call);                                                                    \
+        if (r_ != ncclSuccess) return set_err("NCCL error at %s:%d: %s", __FILE__, __LINE__, ncclGetErrorString(r_)); \
+    } while (0)
+#define TRY(call)                   \
+    do {                            \
+        int rc_ = (call);           \
+        if (rc_) return rc_;        \
+    } while (0)
+
+struct Level {
+    LevelView v;
+    double *buf[3];         /* SARASMG_PRESSURE, SARASMG_RESIDUAL, SARASMG_TMP */
+    double *met[6];         /* device metric arrays (padded, base -1) */
+    size_t elems;           /* allocated doubles per array */
+};
+
+struct ProfEntry { int kind, level, bucket; cudaEvent_t a, b; };
+
+struct sarasmg_solver_s {
+    sarasmg_desc d;
+    bool planar;
+    int D;
+    std::vector<Level> lev;
+    int vLevel;
+    int zeroBC;
+    int maxCount;
+    cudaStream_t st;
+    double *d_wall[3];
+    double *d_part;             /* reduction scratch */
+    size_t part_cap;
+    double *d_scal;             /* small device scalars */
+    double *h_scal;             /* pinned host mirror */
+    int *d_iters;               /* coarse-solve iteration count */
+    int *h_iters;
+    double *d_in_p, *d_in_rhs;  /* device-resident inputs of sarasmg_solve_resident */
+    /* inter-GPU halo */
+    ncclComm_t comm;
+    bool has_comm;
+    double *xs[2], *xr[2], *ys[2], *yr[2];
+    double *d_gather;           /* n_proc * 4 doubles */
+    /* instrumentation */
+    long long launches;
+    std::vector<ProfEntry> pending;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[SARASMG_K_COUNT][32];
+    long long prof_n[SARASMG_K_COUNT][32];
+    double t_comp, t_tran;
+    int bucket;                 /* 0 none, 1 smooth-compute, 2 smooth-transfer */
+    cudaEvent_t ev_solve0, ev_solve1;
+    double last_solve_ms;
+    int last_coarse_iters;
+};
+
+typedef sarasmg_solver_s S;
+
+/* ------------------------------------------------------------------------------------------------ */
+/* instrumentation helpers                                                                           */
+/* ------------------------------------------------------------------------------------------------ */
+static int prof_fold(S *s) {
+    if (s->pending.empty()) return 0;
+    CU(cudaStreamSynchronize(s->st));
+    for (auto &e : s->pending) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e.a, e.b));
+        s->prof_ms[e.kind][e.level] += ms;
+        s->prof_n[e.kind][e.level] += 1;
+        if (e.bucket == 1) s->t_comp += ms * 1e-3;
+        if (e.bucket == 2) s->t_tran += ms * 1e-3;
+        s->ev_pool.push_back(e.a);
+        s->ev_pool.push_back(e.b);
+    }
+    s->pending.clear();
+    return 0;
+}
+
+struct ProfScope {
+    S *s;
+    bool on;
+    ProfEntry e;
+    ProfScope(S *s_, int kind, int level) : s(s_) {
+        on = (s->d.flags & (SARASMG_FLAG_PROFILE | SARASMG_FLAG_TIME_RUN)) != 0;
+        if (!on) return;
+        e.kind = kind; e.level = level; e.bucket = s->bucket;
+        for (cudaEvent_t *ev : {&e.a, &e.b}) {
+            if (!s->ev_pool.empty()) { *ev = s->ev_pool.back(); s->ev_pool.pop_back(); }
+            else cudaEventCreate(ev);
+        }
+        cudaEventRecord(e.a, s->st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(e.b, s->st);
+        s->pending.push_back(e);
+        if (s->pending.size() > 8192) prof_fold(s);
+    }
+};
+
+static inline int kcheck(S *s, const char *what) {
+    s->launches += 1;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return set_err("kernel launch %s failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+static inline unsigned face_blocks(long long cnt) { return std::max(1u, std::min(cdiv(cnt, 256), 4096u)); }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* host <-> device copies of a level array (compact padded host layout <-> pitched device layout)    */
+/* ------------------------------------------------------------------------------------------------ */
+static int copy_h2d(S *s, const Level &L, double *dev, const double *host) {
+    CU(cudaMemcpy2DAsync(dev + MG_LEAD, (size_t)L.v.pitch * sizeof(double), host, (size_t)L.v.Fz * sizeof(double),
+                         (size_t)L.v.Fz * sizeof(double), (size_t)L.v.Fx * L.v.Fy, cudaMemcpyHostToDevice, s->st));
+    return 0;
+}
+static int copy_d2h(S *s, const Level &L, double *host, const double *dev) {
+    CU(cudaMemcpy2DAsync(host, (size_t)L.v.Fz * sizeof(double), dev + MG_LEAD, (size_t)L.v.pitch * sizeof(double),
+                         (size_t)L.v.Fz * sizeof(double), (size_t)L.v.Fx * L.v.Fy, cudaMemcpyDeviceToHost, s->st));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* face operations                                                                                   */
+/* ------------------------------------------------------------------------------------------------ */
+static int launch_face(S *s, int dir, double *A, const Level &L, int lo, int hi, const double *wall) {
+    if (lo == FACE_NONE && hi == FACE_NONE) return 0;
+    const LevelView &v = L.v;
+    const int nj = s->planar ? 1 : v.Fy;
+    if (dir == 0) {
+        k_face<0><<<face_blocks((long long)nj * v.Fz), 256, 0, s->st>>>(A, v, lo, hi, wall, s->planar);
+    } else if (dir == 1) {
+        if (s->planar) return 0;
+        k_face<1><<<face_blocks((long long)v.Fx * v.Fz), 256, 0, s->st>>>(A, v, lo, hi, wall, s->planar);
+    } else {
+        k_face<2><<<face_blocks((long long)v.Fx * nj), 256, 0, s->st>>>(A, v, lo, hi, wall, s->planar);
+    }
+    return kcheck(s, "k_face");
+}
+
+static int zero_pads(S *s, int level, double *A) {
+    const Level &L = s->lev[level];
+    ProfScope ps(s, SARASMG_K_MISC, level);
+    TRY(launch_face(s, 0, A, L, FACE_ZERO, FACE_ZERO, nullptr));
+    TRY(launch_face(s, 1, A, L, FACE_ZERO, FACE_ZERO, nullptr));
+    TRY(launch_face(s, 2, A, L, FACE_ZERO, FACE_ZERO, nullptr));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* updatePads (d3:671-686, d2:467-478).  x faces first, then y faces (which carry the fresh x pads):  */
+/* the program order of the reference's blocking self-sends, made deterministic for real neighbours.  */
+/* Neighbour == own rank (periodic, one rank along that axis): local copy kernel.                      */
+/* Neighbour == other rank: pack -> grouped ncclSend/ncclRecv -> unpack on the solver stream.          */
+/* ------------------------------------------------------------------------------------------------ */
+static int update_pads(S *s, int level, double *A) {
+    const Level &L = s->lev[level];
+    const LevelView &v = L.v;
+    const int me = s->d.rank;
+    const int *fr = s->d.face_ranks;
+    ProfScope ps(s, SARASMG_K_HALO, level);
+
+    /* ---- x phase ---- */
+    {
+        const int lo = (fr[0] == me) ? FACE_PERIODIC : FACE_NONE;   /* my i=-1 <- (self) i=xEnd-1 */
+        const int hi = (fr[1] == me) ? FACE_PERIODIC : FACE_NONE;   /* my i=xEnd+1 <- (self) i=1 */
+        TRY(launch_face(s, 0, A, L, lo, hi, nullptr));
+        const bool rl = (fr[0] != SARASMG_PROC_NULL && fr[0] != me);
+        const bool rr = (fr[1] != SARASMG_PROC_NULL && fr[1] != me);
+        if (rl || rr) {
+            if (!s->has_comm) return set_err("update_pads: remote neighbour but no NCCL communicator");
+            const int nj = s->planar ? 1 : v.Fy;
+            const long long cnt = (long long)nj * v.Fz;
+            const unsigned nb = face_blocks(cnt);
+            if (rl) { k_pack_x<<<nb, 256, 0, s->st>>>(A, v, 1, s->planar, s->xs[0]); TRY(kcheck(s, "k_pack_x")); }
+            if (rr) { k_pack_x<<<nb, 256, 0, s->st>>>(A, v, v.nx - 2, s->planar, s->xs[1]); TRY(kcheck(s, "k_pack_x")); }
+            NC(ncclGroupStart());
+            /* order: (send left, recv right), (send right, recv left): keeps pairs matched when both neighbours are one peer */
+            if (rl) NC(ncclSend(s->xs[0], (size_t)cnt, ncclDouble, fr[0], s->comm, s->st));
+            if (rr) NC(ncclRecv(s->xr[1], (size_t)cnt, ncclDouble, fr[1], s->comm, s->st));
+            if (rr) NC(ncclSend(s->xs[1], (size_t)cnt, ncclDouble, fr[1], s->comm, s->st));
+            if (rl) NC(ncclRecv(s->xr[0], (size_t)cnt, ncclDouble, fr[0], s->comm, s->st));
+            NC(ncclGroupEnd());
+            if (rl) { k_unpack_x<<<nb, 256, 0, s->st>>>(A, v, -1, s->planar, s->xr[0]); TRY(kcheck(s, "k_unpack_x")); }
+            if (rr) { k_unpack_x<<<nb, 256, 0, s->st>>>(A, v, v.nx, s->planar, s->xr[1]); TRY(kcheck(s, "k_unpack_x")); }
+        }
+    }
+    if (s->planar) return 0;
+
+    /* ---- y phase ---- */
+    {
+        const int lo = (fr[2] == me) ? FACE_PERIODIC : FACE_NONE;
+        const int hi = (fr[3] == me) ? FACE_PERIODIC : FACE_NONE;
+        TRY(launch_face(s, 1, A, L, lo, hi, nullptr));
+        const bool rf = (fr[2] != SARASMG_PROC_NULL && fr[2] != me);
+        const bool rb = (fr[3] != SARASMG_PROC_NULL && fr[3] != me);
+        if (rf || rb) {
+            if (!s->has_comm) return set_err("update_pads: remote neighbour but no NCCL communicator");
+            const long long cnt = (long long)v.Fx * v.Fz;
+            const unsigned nb = face_blocks(cnt);
+            if (rf) { k_pack_y<<<nb, 256, 0, s->st>>>(A, v, 1, s->ys[0]); TRY(kcheck(s, "k_pack_y")); }
+            if (rb) { k_pack_y<<<nb, 256, 0, s->st>>>(A, v, v.ny - 2, s->ys[1]); TRY(kcheck(s, "k_pack_y")); }
+            NC(ncclGroupStart());
+            if (rf) NC(ncclSend(s->ys[0], (size_t)cnt, ncclDouble, fr[2], s->comm, s->st));
+            if (rb) NC(ncclRecv(s->yr[1], (size_t)cnt, ncclDouble, fr[3], s->comm, s->st));
+            if (rb) NC(ncclSend(s->ys[1], (size_t)cnt, ncclDouble, fr[3], s->comm, s->st));
+            if (rf) NC(ncclRecv(s->yr[0], (size_t)cnt, ncclDouble, fr[2], s->comm, s->st));
+            NC(ncclGroupEnd());
+            if (rf) { k_unpack_y<<<nb, 256, 0, s->st>>>(A, v, -1, s->yr[0]); TRY(kcheck(s, "k_unpack_y")); }
+            if (rb) { k_unpack_y<<<nb, 256, 0, s->st>>>(A, v, v.ny, s->yr[1]); TRY(kcheck(s, "k_unpack_y")); }
+        }
+    }
+    return 0;
+}
+
+/* wall-BC modes of this rank (imposeBC d3:578-667, d2:406-463) */
+static void bc_modes(const S *s, int m[6]) {
+    const sarasmg_desc &d = s->d;
+    const int wall = d.test_poisson ? (s->zeroBC ? FACE_NEG_MIRROR : FACE_WALL) : FACE_MIRROR;
+    for (int q = 0; q < 6; q++) m[q] = FACE_NONE;
+    if (!d.x_per) {
+        if (d.x_rank == 0) m[0] = wall;
+        if (d.x_rank == d.npx - 1) m[1] = wall;
+    }
+    if (!s->planar && !d.y_per) {
+        if (d.y_rank == 0) m[2] = wall;
+        if (d.y_rank == d.npy - 1) m[3] = wall;
+    }
+    if (d.z_per) { m[4] = FACE_PERIODIC; m[5] = FACE_PERIODIC; }
+    else { m[4] = wall; m[5] = wall; }
+}
+
+static int impose_bc(S *s, int level) {
+    const Level &L = s->lev[level];
+    double *P = L.buf[SARASMG_PRESSURE];
+    TRY(update_pads(s, level, P));
+    int m[6];
+    bc_modes(s, m);
+    if ((m[0] == FACE_WALL || m[2] == FACE_WALL || m[4] == FACE_WALL) && level != 0)
+        return set_err("imposeBC: non-homogeneous Dirichlet BC requested on level %d (wall arrays exist on level 0 only)", level);
+    ProfScope ps(s, SARASMG_K_BC, level);
+    TRY(launch_face(s, 0, P, L, m[0], m[1], s->d_wall[0]));
+    TRY(launch_face(s, 1, P, L, m[2], m[3], s->d_wall[1]));
+    TRY(launch_face(s, 2, P, L, m[4], m[5], s->d_wall[2]));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* marching-kernel launch geometry                                                                   */
+/* ------------------------------------------------------------------------------------------------ */
+struct MarchGeom { dim3 grid, block; int ichunk; };
+
+static MarchGeom march_geom(const S *s, const LevelView &v) {
+    MarchGeom g;
+    const int pairs = (v.nz + 1) / 2;
+    int bx = 32, by = 8;
+    if (s->planar) { bx = 128; by = 1; }
+    else {
+        while (bx > 4 && bx / 2 >= pairs) { bx /= 2; by *= 2; }
+    }
+    g.block = dim3(bx, by, 1);
+    const unsigned gx = cdiv(pairs, bx), gy = s->planar ? 1 : cdiv(v.ny, by);
+    /* pick the x-chunk so that the grid has >= ~8 CTAs per SM (148 SMs) when the level is big enough */
+    int ichunk = 64;
+    while (ichunk > 4 && (long long)gx * gy * cdiv(v.nx, ichunk) < 148LL * 8) ichunk /= 2;
+    g.ichunk = ichunk;
+    g.grid = dim3(gx, gy, cdiv(v.nx, ichunk));
+    return g;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* operators                                                                                         */
+/* ------------------------------------------------------------------------------------------------ */
+static int gs_sweep(S *s, int level) {
+    Level &L = s->lev[level];
+    const LevelView &v = L.v;
+    double *P = L.buf[SARASMG_PRESSURE];
+    const double *R = L.buf[SARASMG_RESIDUAL];
+    if (!s->planar) {
+        const int H = v.nx + v.ny + v.nz - 2;
+        for (int h = 0; h < H; ++h) {
+            const int ilo = std::max(0, h - (v.ny - 1) - (v.nz - 1));
+            const int ihi = std::min(v.nx - 1, h);
+            dim3 block(32, 8, 1);
+            dim3 grid(cdiv(v.ny, 32), cdiv(ihi - ilo + 1, 8), 1);
+            k_gs_plane<3><<<grid, block, 0, s->st>>>(P, R, v, h, ilo);
+            TRY(kcheck(s, "k_gs_plane<3>"));
+        }
+    } else {
+        const int H = v.nx + v.nz - 1;
+        for (int h = 0; h < H; ++h) {
+            const int ilo = std::max(0, h - (v.nz - 1));
+            const int ihi = std::min(v.nx - 1, h);
+            k_gs_plane<2><<<cdiv(ihi - ilo + 1, 128), 128, 0, s->st>>>(P, R, v, h, ilo);
+            TRY(kcheck(s, "k_gs_plane<2>"));
+        }
+    }
+    return 0;
+}
+
+/* smooth (d3:114-187, d2:109-147) */
+static int op_smooth(S *s, int count) {
+    const int l = s->vLevel;
+    Level &L = s->lev[l];
+    for (int n = 0; n < count; ++n) {
+        s->bucket = 2;
+        TRY(impose_bc(s, l));
+        s->bucket = 1;
+        {
+            ProfScope ps(s, SARASMG_K_SMOOTH, l);
+            if (s->d.gs_smooth) {
+                TRY(gs_sweep(s, l));
+            } else {
+                const MarchGeom g = march_geom(s, L.v);
+                if (s->planar) k_stencil_march<2, 0><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
+                else k_stencil_march<3, 0><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
+                TRY(kcheck(s, "k_stencil_march<jacobi>"));
+                std::swap(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_TMP]);      /* d3:168 */
+            }
+        }
+        s->bucket = 0;
+    }
+    s->bucket = 2;
+    TRY(impose_bc(s, l));
+    s->bucket = 0;
+    return 0;
+}
+
+/* computeResidual (d3:90-111, d2:90-106) */
+static int op_compute_residual(S *s) {
+    const int l = s->vLevel;
+    Level &L = s->lev[l];
+    TRY(zero_pads(s, l, L.buf[SARASMG_TMP]));
+    {
+        ProfScope ps(s, SARASMG_K_RESIDUAL, l);
+        const MarchGeom g = march_geom(s, L.v);
+        if (s->planar) k_stencil_march<2, 1><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
+        else k_stencil_march<3, 1><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
+        TRY(kcheck(s, "k_stencil_march<residual>"));
+    }
+    TRY(update_pads(s, l, L.buf[SARASMG_TMP]));
+    return 0;
+}
+
+/* coarsen (d3:250-298, d2:202-236): vLevel += 1 */
+static int op_coarsen(S *s) {
+    const int pLevel = s->vLevel;
+    if (pLevel >= s->D) return set_err("coarsen: already at the coarsest level");
+    s->vLevel += 1;
+    Level &Lf = s->lev[pLevel];
+    Level &Lc = s->lev[s->vLevel];
+    ProfScope ps(s, SARASMG_K_COARSEN, pLevel);
+    if (s->planar) {
+        k_coarsen<2><<<dim3(cdiv(Lc.v.nz, 128), 1, Lc.v.nx), dim3(128, 1, 1), 0, s->st>>>(Lf.buf[SARASMG_TMP], Lf.v, Lc.buf[SARASMG_RESIDUAL], Lc.v);
+    } else {
+        int bx = 64, by = 4;
+        while (bx > 4 && bx / 2 >= Lc.v.nz) { bx /= 2; by *= 2; }
+        k_coarsen<3><<<dim3(cdiv(Lc.v.nz, bx), cdiv(Lc.v.ny, by), Lc.v.nx), dim3(bx, by, 1), 0, s->st>>>(Lf.buf[SARASMG_TMP], Lf.v, Lc.buf[SARASMG_RESIDUAL], Lc.v);
+    }
+    return kcheck(s, "k_coarsen");
+}
+
+/* prolong (d3:301-365, d2:239-271) fused with pressureData += smoothedPres (p:271): vLevel -= 1 */
+static int op_prolong(S *s) {
+    const int pLevel = s->vLevel;
+    if (pLevel <= 0) return set_err("prolong: already at the finest level");
+    s->vLevel -= 1;
+    Level &Lc = s->lev[pLevel];
+    Level &Lf = s->lev[s->vLevel];
+    ProfScope ps(s, SARASMG_K_PROLONG, s->vLevel);
+    if (s->planar) {
+        k_prolong_add<2><<<dim3(cdiv(Lf.v.nz, 128), 1, Lf.v.nx), dim3(128, 1, 1), 0, s->st>>>(Lc.buf[SARASMG_PRESSURE], Lc.v, Lf.buf[SARASMG_PRESSURE], Lf.v);
+    } else {
+        int bx = 64, by = 4;
+        while (bx > 4 && bx / 2 >= Lf.v.nz) { bx /= 2; by *= 2; }
+        k_prolong_add<3><<<dim3(cdiv(Lf.v.nz, bx), cdiv(Lf.v.ny, by), Lf.v.nx), dim3(bx, by, 1), 0, s->st>>>(Lc.buf[SARASMG_PRESSURE], Lc.v, Lf.buf[SARASMG_PRESSURE], Lf.v);
+    }
+    return kcheck(s, "k_prolong_add");
+}
+
+static int ensure_part(S *s, size_t n) {
+    if (n <= s->part_cap) return 0;
+    if (s->d_part) CU(cudaFree(s->d_part));
+    s->part_cap = std::max(n, (size_t)1 << 16);
+    CU(cudaMalloc(&s->d_part, s->part_cap * sizeof(double)));
+    return 0;
+}
+
+/* gather `nq` per-rank doubles (already in d_scal[0..nq)) from every rank into h (n_proc*nq), rank order */
+static int gather_scalars(S *s, int nq, std::vector<double> &out) {
+    const int np = s->d.n_proc;
+    out.assign((size_t)np * nq, 0.0);
+    if (np == 1 || !s->has_comm) {
+        CU(cudaMemcpyAsync(s->h_scal, s->d_scal, nq * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        for (int q = 0; q < nq; q++) out[q] = s->h_scal[q];
+        return 0;
+    }
+    NC(ncclAllGather(s->d_scal, s->d_gather, (size_t)nq, ncclDouble, s->comm, s->st));
+    CU(cudaMemcpyAsync(s->h_scal, s->d_gather, (size_t)np * nq * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    for (int q = 0; q < np * nq; q++) out[q] = s->h_scal[q];
+    return 0;
+}
+
+/* computeError (d3:391-459, d2:274-338); sums over ranks in rank order */
+static int op_compute_error(S *s, int norm, double *value) {
+    *value = 0.0;
+    if (norm != 1 && norm != 2) return 0;           /* resType 0: returns 0 (d3:392,418) */
+    Level &L = s->lev[0];
+    const MarchGeom g = march_geom(s, L.v);
+    const int nb = g.grid.x * g.grid.y * g.grid.z;
+    TRY(ensure_part(s, (size_t)2 * nb + 4096));
+    {
+        ProfScope ps(s, SARASMG_K_ERROR, 0);
+        const Level &Lv = s->lev[s->vLevel];        /* d3:411 uses hx(vLevel) */
+        if (s->planar) k_error_march<2><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, g.ichunk, norm, L.v.hx, L.v.hy, L.v.hz, s->d_part, nb);
+        else k_error_march<3><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, g.ichunk, norm, Lv.v.hx, Lv.v.hy, Lv.v.hz, s->d_part, nb);
+        TRY(kcheck(s, "k_error_march"));
+        k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part, nb, 2, (norm == 1) ? 1u : 0u, s->d_scal);
+        TRY(kcheck(s, "k_reduce_final"));
+        if (norm == 1) {
+            /* denominator: max |rhs| over the whole padded array (d3:437) */
+            const unsigned nbp = std::min(cdiv((long long)L.v.Fx * L.v.Fy, 4), 2048u);
+            k_reduce_padded<1><<<nbp, 256, 0, s->st>>>(L.buf[SARASMG_RESIDUAL], L.v, s->d_part);
+            TRY(kcheck(s, "k_reduce_padded"));
+            k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part, (int)nbp, 1, 1u, s->d_scal + 1);
+            TRY(kcheck(s, "k_reduce_final"));
+        }
+    }
+    std::vector<double> g2;
+    TRY(gather_scalars(s, 2, g2));
+    const int np = s->d.n_proc;
+    const long long cnt_loc = (long long)L.v.nx * L.v.ny * L.v.nz;
+    if (norm == 1) {
+        double num = g2[0], den = g2[1];
+        for (int r = 1; r < np; r++) { num = std::max(num, g2[2 * r]); den = std::max(den, g2[2 * r + 1]); }
+        *value = den ? num / den : num;
+    } else {
+        double num = 0.0, den = 0.0;
+        for (int r = 0; r < np; r++) { num += g2[2 * r]; den += g2[2 * r + 1]; }
+        const int cnt = (int)(cnt_loc * np);        /* valCountGlo is an int in the reference (d3:434) */
+        *value = den ? std::sqrt(num / cnt) / std::sqrt(den / cnt) : std::sqrt(num / cnt);
+    }
+    return 0;
+}
+
+static void bc_plan(const S *s, BcPlan &B) {
+    int m[6];
+    bc_modes(s, m);
+    const int me = s->d.rank;
+    const int *fr = s->d.face_ranks;
+    B.pad_x_lo = (fr[0] == me) ? FACE_PERIODIC : FACE_NONE;
+    B.pad_x_hi = (fr[1] == me) ? FACE_PERIODIC : FACE_NONE;
+    B.pad_y_lo = (!s->planar && fr[2] == me) ? FACE_PERIODIC : FACE_NONE;
+    B.pad_y_hi = (!s->planar && fr[3] == me) ? FACE_PERIODIC : FACE_NONE;
+    B.bc_x_lo = m[0]; B.bc_x_hi = m[1]; B.bc_y_lo = m[2]; B.bc_y_hi = m[3]; B.bc_z_lo = m[4]; B.bc_z_hi = m[5];
+    B.xwall = s->d_wall[0]; B.ywall = s->d_wall[1]; B.zwall = s->d_wall[2];
+    B.planar = s->planar;
+}
+
+/* solve (d3:190-247, d2:150-199) */
+static int op_solve_coarsest(S *s, int *iters, bool sync) {
+    const int l = s->vLevel;
+    Level &L = s->lev[l];
+    const sarasmg_desc &d = s->d;
+    const int *fr = d.face_ranks;
+    bool remote = false;
+    for (int f = 0; f < 4; f++) if (fr[f] != SARASMG_PROC_NULL && fr[f] != d.rank) remote = true;
+    ProfScope ps(s, SARASMG_K_COARSE_SOLVE, l);
+    if (d.n_proc == 1 || (!remote && !s->has_comm)) {
+        BcPlan B;
+        bc_plan(s, B);
+        if ((B.bc_x_lo == FACE_WALL || B.bc_y_lo == FACE_WALL || B.bc_z_lo == FACE_WALL) && l != 0)
+            return set_err("solve: non-homogeneous Dirichlet BC on level %d", l);
+        if (s->planar) k_coarse_solve<2><<<1, 1024, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, B, d.mg_tolerance, s->maxCount, s->d_iters);
+        else k_coarse_solve<3><<<1, 1024, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, B, d.mg_tolerance, s->maxCount, s->d_iters);
+        TRY(kcheck(s, "k_coarse_solve"));
+        CU(cudaMemcpyAsync(s->h_iters, s->d_iters, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+        if (sync) {
+            CU(cudaStreamSynchronize(s->st));
+            if (iters) *iters = *s->h_iters;
+            s->last_coarse_iters = *s->h_iters;
+        }
+        return 0;
+    }
+    /* several ranks: host-driven loop, one halo exchange and one MAX all-reduce per iteration (d3:195,233) */
+    int iterCount = 0;
+    const long long cnt = (long long)L.v.nx * L.v.ny * L.v.nz;
+    const unsigned nb = std::min(cdiv(cnt, 256), 1024u);
+    TRY(ensure_part(s, nb));
+    while (true) {
+        TRY(impose_bc(s, l));
+        TRY(gs_sweep(s, l));
+        if (s->planar) k_resid_max<2><<<nb, 256, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, s->d_part);
+        else k_resid_max<3><<<nb, 256, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, s->d_part);
+        TRY(kcheck(s, "k_resid_max"));
+        k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part, (int)nb, 1, 1u, s->d_scal);
+        TRY(kcheck(s, "k_reduce_final"));
+        std::vector<double> g1;
+        TRY(gather_scalars(s, 1, g1));
+        double globalMax = g1[0];
+        for (int r = 1; r < d.n_proc; r++) globalMax = std::max(globalMax, g1[r]);
+        if (globalMax < d.mg_tolerance) break;
+        iterCount += 1;
+        if (iterCount > s->maxCount) {
+            if (d.print_residual && d.rank == 0) printf("WARNING: Iterations for solution at coarsest level not converging.\n");
+            break;
+        }
+    }
+    TRY(impose_bc(s, l));
+    if (iters) *iters = iterCount;
+    s->last_coarse_iters = iterCount;
+    *s->h_iters = iterCount;
+    return 0;
+}
+
+/* vCycle (p:219-280) */
+static int op_vcycle(S *s, int *coarse_iters) {
+    const int D = s->D;
+    s->vLevel = 0;
+    s->zeroBC = 0;
+    TRY(op_smooth(s, s->d.pre_smooth));
+    s->zeroBC = 1;
+    for (int i = 0; i < D; i++) {
+        TRY(op_compute_residual(s));
+        /* p:252 smoothedPres = pressureData: kept in place (see header comment) */
+        TRY(op_coarsen(s));
+        {   /* p:258 pressureData(vLevel) = 0 */
+            Level &L = s->lev[s->vLevel];
+            ProfScope ps(s, SARASMG_K_MISC, s->vLevel);
+            CU(cudaMemsetAsync(L.buf[SARASMG_PRESSURE], 0, L.elems * sizeof(double), s->st));
+        }
+        if (s->vLevel == D) TRY(op_solve_coarsest(s, nullptr, false));
+        else TRY(op_smooth(s, s->d.pre_smooth));
+    }
+    for (int i = 0; i < D; i++) {
+        TRY(op_prolong(s));
+        s->zeroBC = (s->vLevel == 0) ? 0 : 1;
+        TRY(op_smooth(s, s->d.post_smooth));
+    }
+    (void)coarse_iters;
+    return 0;
+}
+
+/* everything mgSolve does between the host copies (p:105-148), from the device input buffers */
+static int solve_core(S *s, const double *in_p, const double *in_rhs, int *cycles_done, double *hist, int *citers) {
+    const sarasmg_desc &d = s->d;
+    Level &L0 = s->lev[0];
+    s->vLevel = 0;
+    /* p:107-111: zero the hierarchy (smoothedPres has no storage; tmpDataArray is not zeroed here either) */
+    for (int l = 0; l <= s->D; l++) {
+        Level &L = s->lev[l];
+        CU(cudaMemsetAsync(L.buf[SARASMG_PRESSURE], 0, L.elems * sizeof(double), s->st));
+        CU(cudaMemsetAsync(L.buf[SARASMG_RESIDUAL], 0, L.elems * sizeof(double), s->st));
+    }
+    /* p:114-115: core of rhs -> residualData(0), core of inFn -> pressureData(0) */
+    {
+        dim3 grid(cdiv(L0.v.nz, 128), L0.v.ny, L0.v.nx);
+        k_copy_core<<<grid, 128, 0, s->st>>>(in_rhs, L0.buf[SARASMG_RESIDUAL], L0.v);
+        TRY(kcheck(s, "k_copy_core"));
+        k_copy_core<<<grid, 128, 0, s->st>>>(in_p, L0.buf[SARASMG_PRESSURE], L0.v);
+        TRY(kcheck(s, "k_copy_core"));
+    }
+    TRY(update_pads(s, 0, L0.buf[SARASMG_RESIDUAL]));       /* p:117 */
+    TRY(update_pads(s, 0, L0.buf[SARASMG_PRESSURE]));       /* p:118 */
+
+    if (!d.test_poisson) {                                  /* p:120-129 */
+        const unsigned nbp = std::min(cdiv((long long)L0.v.Fx * L0.v.Fy, 4), 2048u);
+        TRY(ensure_part(s, nbp));
+        k_reduce_padded<0><<<nbp, 256, 0, s->st>>>(L0.buf[SARASMG_RESIDUAL], L0.v, s->d_part);
+        TRY(kcheck(s, "k_reduce_padded"));
+        k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part, (int)nbp, 1, 0u, s->d_scal);
+        TRY(kcheck(s, "k_reduce_final"));
+        std::vector<double> sums;
+        TRY(gather_scalars(s, 1, sums));
+        const double cnt = (double)((long long)L0.v.Fx * L0.v.Fy * L0.v.Fz);
+        double globalAvg = 0.0;
+        for (int r = 0; r < d.n_proc; r++) globalAvg += sums[r] / cnt;      /* sum of local means, rank order */
+        globalAvg /= d.n_proc;
+        k_sub_scalar_padded<<<nbp, 256, 0, s->st>>>(L0.buf[SARASMG_RESIDUAL], L0.v, globalAvg);
+        TRY(kcheck(s, "k_sub_scalar_padded"));
+    }
+
+    double prevResidual = 0.0;
+    int cycles = 0;
+    CU(cudaEventRecord(s->ev_solve0, s->st));
+    for (int i = 0; i < d.vc_count; i++) {                  /* p:132-148 */
+        *s->h_iters = 0;
+        TRY(op_vcycle(s, nullptr));
+        double mgResidual = 0.0;
+        TRY(op_compute_error(s, d.res_type, &mgResidual));
+        if (d.res_type == 0) CU(cudaStreamSynchronize(s->st));
+        s->last_coarse_iters = *s->h_iters;
+        if (s->last_coarse_iters > s->maxCount && d.n_proc == 1 && d.print_residual && d.rank == 0)
+            printf("WARNING: Iterations for solution at coarsest level not converging.\n");    /* d3:240-243 */
+        if (hist) hist[i] = mgResidual;
+        if (citers) citers[i] = s->last_coarse_iters;
+        cycles = i + 1;
+        if (d.print_residual && d.rank == 0) {
+            if (d.test_poisson) printf("\nResidual after V Cycle %d is %.16g\n", i, mgResidual);
+            else printf("\nResidual after V Cycle %d is %g\n", i, mgResidual);
+        }
+        if (!d.test_poisson) {
+            if (std::fabs(prevResidual - mgResidual) < d.mg_tolerance) break;
+            prevResidual = mgResidual;
+        }
+    }
+    CU(cudaEventRecord(s->ev_solve1, s->st));
+    CU(cudaEventSynchronize(s->ev_solve1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev_solve0, s->ev_solve1));
+    s->last_solve_ms = ms;
+    if (cycles_done) *cycles_done = cycles;
+    return 0;
+}
+
+static int analytic_deviation(S *s, double *out) {
+    Level &L0 = s->lev[0];
+    const sarasmg_desc &d = s->d;
+    const int ubx = L0.v.nx - 1, uby = L0.v.ny - 1;
+    const long long cnt = (long long)L0.v.nx * L0.v.ny * L0.v.nz;
+    const unsigned nb = std::min(cdiv(cnt, 256), 2048u);
+    TRY(ensure_part(s, nb));
+    k_analytic_dev<<<nb, 256, 0, s->st>>>(L0.buf[SARASMG_PRESSURE], L0.v, d.dim, d.x_rank * ubx, d.y_rank * uby,
+                                          ubx * d.npx / 2, uby * d.npy / 2, s->d_part);
+    TRY(kcheck(s, "k_analytic_dev"));
+    k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part, (int)nb, 1, 1u, s->d_scal);
+    TRY(kcheck(s, "k_reduce_final"));
+    std::vector<double> g;
+    TRY(gather_scalars(s, 1, g));
+    double m = g[0];
+    for (int r = 1; r < d.n_proc; r++) m = std::max(m, g[r]);
+    *out = m;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* extern "C"                                                                                        */
+/* ------------------------------------------------------------------------------------------------ */
+extern "C" {
+
+const char *sarasmg_last_error(void) { return g_err.c_str(); }
+int sarasmg_version(void) { return 100; }
+
+int sarasmg_get_unique_id(void *out) {
+    static_assert(sizeof(ncclUniqueId) == SARASMG_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NC(ncclGetUniqueId(&id));
+    memcpy(out, &id, sizeof(id));
+    return 0;
+}
+
+int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
+    if (!desc || !out) return set_err("sarasmg_create: null argument");
+    if (desc->dim != 2 && desc->dim != 3) return set_err("sarasmg_create: dim must be 2 or 3");
+    if (desc->vc_depth < 0 || desc->vc_depth > 30) return set_err("sarasmg_create: bad vc_depth");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return set_err("sarasmg_create: no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(ce));
+    CU(cudaSetDevice(desc->device));
+
+    S *s = new S();
+    s->d = *desc;
+    s->planar = (desc->dim == 2);
+    s->D = desc->vc_depth;
+    s->vLevel = 0; s->zeroBC = 0;
+    s->d_part = nullptr; s->part_cap = 0;
+    s->d_in_p = s->d_in_rhs = nullptr;
+    s->has_comm = false;
+    s->launches = 0;
+    s->t_comp = s->t_tran = 0.0; s->bucket = 0;
+    s->last_solve_ms = 0.0; s->last_coarse_iters = 0;
+    memset(s->prof_ms, 0, sizeof(s->prof_ms));
+    memset(s->prof_n, 0, sizeof(s->prof_n));
+    for (int q = 0; q < 3; q++) s->d_wall[q] = nullptr;
+    for (int q = 0; q < 2; q++) s->xs[q] = s->xr[q] = s->ys[q] = s->yr[q] = nullptr;
+    s->d_gather = nullptr;
+    CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev_solve0));
+    CU(cudaEventCreate(&s->ev_solve1));
+
+    const int D = s->D;
+    s->lev.resize(D + 1);
+    size_t moff[3] = {0, 0, 0};
+    for (int l = 0; l <= D; l++) {
+        Level &L = s->lev[l];
+        LevelView &v = L.v;
+        int n[3];
+        for (int dd = 0; dd < 3; dd++) {
+            const int n0 = desc->n0[dd];
+            if (s->planar && dd == 1) { n[dd] = 1; continue; }
+            if (((n0 - 1) >> l) << l != (n0 - 1) || ((n0 - 1) >> l) < 2)
+                return set_err("sarasmg_create: level-0 size %d along axis %d cannot be coarsened %d times (need >= 3 points, parser.cc:307-337)", n0, dd, l);
+            n[dd] = ((n0 - 1) >> l) + 1;
+        }
+        v.nx = n[0]; v.ny = n[1]; v.nz = n[2];
+        v.Fx = n[0] + 2; v.Fy = n[1] + 2; v.Fz = n[2] + 2;
+        v.pitch = ((v.nz + 6 + 3) / 4) * 4;
+        v.plane = (long long)v.Fy * v.pitch;
+        L.elems = (size_t)v.Fx * v.plane + 16;
+        for (int a = 0; a < 3; a++) {
+            CU(cudaMalloc(&L.buf[a], L.elems * sizeof(double)));
+            CU(cudaMemsetAsync(L.buf[a], 0, L.elems * sizeof(double), s->st));
+        }
+        v.hx = desc->hx ? desc->hx[l] : 0.0;   v.hy = desc->hy ? desc->hy[l] : 0.0;   v.hz = desc->hz ? desc->hz[l] : 0.0;
+        v.hx2 = desc->hx2 ? desc->hx2[l] : 0.0; v.hz2 = desc->hz2 ? desc->hz2[l] : 0.0; v.hzhx = desc->hzhx ? desc->hzhx[l] : 0.0;
+        v.hxhy = desc->hxhy ? desc->hxhy[l] : 0.0; v.hyhz = desc->hyhz ? desc->hyhz[l] : 0.0; v.hxhyhz = desc->hxhyhz ? desc->hxhyhz[l] : 0.0;
+        const double *src[6] = {desc->xixx, desc->xix2, desc->etyy, desc->ety2, desc->ztzz, desc->ztz2};
+        const int Fd[3] = {v.Fx, v.Fy, v.Fz};
+        for (int m = 0; m < 6; m++) {
+            const int dd = m / 2;
+            CU(cudaMalloc(&L.met[m], (size_t)(Fd[dd] + 2) * sizeof(double)));
+            CU(cudaMemsetAsync(L.met[m], 0, (size_t)(Fd[dd] + 2) * sizeof(double), s->st));
+            if (src[m] && !(s->planar && dd == 1))
+                CU(cudaMemcpyAsync(L.met[m], src[m] + moff[dd], (size_t)Fd[dd] * sizeof(double), cudaMemcpyHostToDevice, s->st));
+        }
+        for (int dd = 0; dd < 3; dd++) moff[dd] += (size_t)Fd[dd];
+        v.xixx = L.met[0] + 1; v.xix2 = L.met[1] + 1; v.etyy = L.met[2] + 1; v.ety2 = L.met[3] + 1; v.ztzz = L.met[4] + 1; v.ztz2 = L.met[5] + 1;
+    }
+    {   /* p:360-361 maxCount */
+        const LevelView &v = s->lev[D].v;
+        s->maxCount = (v.Fx - 1) * (v.Fy - 1) * (v.Fz - 1);
+    }
+    {   /* Dirichlet planes */
+        const LevelView &v0 = s->lev[0].v;
+        size_t wn[3];
+        if (!s->planar) { wn[0] = (size_t)v0.Fy * v0.Fz; wn[1] = (size_t)v0.Fx * v0.Fz; wn[2] = (size_t)v0.Fx * v0.Fy; }
+        else { wn[0] = (size_t)v0.Fz; wn[1] = 0; wn[2] = (size_t)v0.Fx; }
+        const double *ws[3] = {desc->x_wall, desc->y_wall, desc->z_wall};
+        for (int q = 0; q < 3; q++) {
+            if (desc->test_poisson && wn[q]) {
+                if (!ws[q]) return set_err("sarasmg_create: test_poisson needs wall array %d", q);
+                CU(cudaMalloc(&s->d_wall[q], wn[q] * sizeof(double)));
+                CU(cudaMemcpyAsync(s->d_wall[q], ws[q], wn[q] * sizeof(double), cudaMemcpyHostToDevice, s->st));
+            }
+        }
+    }
+    CU(cudaMalloc(&s->d_scal, 64 * sizeof(double)));
+    CU(cudaMallocHost(&s->h_scal, (size_t)std::max(64, 8 * desc->n_proc) * sizeof(double)));
+    CU(cudaMalloc(&s->d_iters, sizeof(int)));
+    CU(cudaMemsetAsync(s->d_iters, 0, sizeof(int), s->st));
+    CU(cudaMallocHost(&s->h_iters, sizeof(int)));
+    *s->h_iters = 0;
+    TRY(ensure_part(s, 1 << 16));
+
+    if (desc->n_proc > 1) {
+        if (!desc->nccl_id) return set_err("sarasmg_create: n_proc > 1 needs nccl_id");
+        ncclUniqueId id;
+        memcpy(&id, desc->nccl_id, sizeof(id));
+        NC(ncclCommInitRank(&s->comm, desc->n_proc, id, desc->rank));
+        s->has_comm = true;
+        const LevelView &v0 = s->lev[0].v;
+        const size_t xc = (size_t)v0.Fy * v0.Fz, yc = (size_t)v0.Fx * v0.Fz;
+        for (int q = 0; q < 2; q++) {
+            CU(cudaMalloc(&s->xs[q], xc * sizeof(double))); CU(cudaMalloc(&s->xr[q], xc * sizeof(double)));
+            CU(cudaMalloc(&s->ys[q], yc * sizeof(double))); CU(cudaMalloc(&s->yr[q], yc * sizeof(double)));
+        }
+        CU(cudaMalloc(&s->d_gather, (size_t)desc->n_proc * 8 * sizeof(double)));
+    }
+    s->d.nccl_id = nullptr;     /* the caller's buffers are not retained */
+    s->d.hx = s->d.hy = s->d.hz = s->d.hx2 = s->d.hz2 = s->d.hzhx = s->d.hxhy = s->d.hyhz = s->d.hxhyhz = nullptr;
+    s->d.xixx = s->d.xix2 = s->d.etyy = s->d.ety2 = s->d.ztzz = s->d.ztz2 = nullptr;
+    s->d.x_wall = s->d.y_wall = s->d.z_wall = nullptr;
+    CU(cudaStreamSynchronize(s->st));
+    *out = s;
+    return 0;
+}
+
+int sarasmg_destroy(sarasmg_handle s) {
+    if (!s) return 0;
+    cudaSetDevice(s->d.device);
+    cudaStreamSynchronize(s->st);
+    if (s->has_comm) ncclCommDestroy(s->comm);
+    for (auto &L : s->lev) {
+        for (int a = 0; a < 3; a++) cudaFree(L.buf[a]);
+        for (int m = 0; m < 6; m++) cudaFree(L.met[m]);
+    }
+    for (int q = 0; q < 3; q++) if (s->d_wall[q]) cudaFree(s->d_wall[q]);
+    for (int q = 0; q < 2; q++) { cudaFree(s->xs[q]); cudaFree(s->xr[q]); cudaFree(s->ys[q]); cudaFree(s->yr[q]); }
+    cudaFree(s->d_gather);
+    cudaFree(s->d_part); cudaFree(s->d_scal); cudaFree(s->d_iters);
+    cudaFreeHost(s->h_scal); cudaFreeHost(s->h_iters);
+    cudaFree(s->d_in_p); cudaFree(s->d_in_rhs);
+    for (auto &e : s->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto &e : s->ev_pool) cudaEventDestroy(e);
+    cudaEventDestroy(s->ev_solve0); cudaEventDestroy(s->ev_solve1);
+    cudaStreamDestroy(s->st);
+    if ((s->d.flags & SARASMG_FLAG_TIME_RUN) && s->d.rank == 0) {
+        /* poisson::~poisson under -DTIME_RUN (poisson.cc:645-652) */
+        printf("%-50s%.6f\n", "Time taken in computation within smooth: ", s->t_comp);
+        printf("%-50s%.6f\n", "Time taken in data-transfer within smooth: ", s->t_tran);
+    }
+    delete s;
+    return 0;
+}
+
+static int ensure_inputs(S *s) {
+    Level &L0 = s->lev[0];
+    if (!s->d_in_p) {
+        CU(cudaMalloc(&s->d_in_p, L0.elems * sizeof(double)));
+        CU(cudaMalloc(&s->d_in_rhs, L0.elems * sizeof(double)));
+        CU(cudaMemsetAsync(s->d_in_p, 0, L0.elems * sizeof(double), s->st));
+        CU(cudaMemsetAsync(s->d_in_rhs, 0, L0.elems * sizeof(double), s->st));
+    }
+    return 0;
+}
+
+int sarasmg_upload(sarasmg_handle s, const double *p_in, const double *rhs) {
+    if (!s || !p_in || !rhs) return set_err("sarasmg_upload: null argument");
+    CU(cudaSetDevice(s->d.device));
+    TRY(ensure_inputs(s));
+    TRY(copy_h2d(s, s->lev[0], s->d_in_p, p_in));
+    TRY(copy_h2d(s, s->lev[0], s->d_in_rhs, rhs));
+    return 0;
+}
+
+int sarasmg_solve_resident(sarasmg_handle s, int *cycles_done, double *residual_history, int *coarse_iters) {
+    if (!s) return set_err("sarasmg_solve_resident: null handle");
+    if (!s->d_in_p) return set_err("sarasmg_solve_resident: call sarasmg_upload first");
+    CU(cudaSetDevice(s->d.device));
+    return solve_core(s, s->d_in_p, s->d_in_rhs, cycles_done, residual_history, coarse_iters);
+}
+
+int sarasmg_download(sarasmg_handle s, double *p_out) {
+    if (!s || !p_out) return set_err("sarasmg_download: null argument");
+    CU(cudaSetDevice(s->d.device));
+    TRY(copy_d2h(s, s->lev[0], p_out, s->lev[0].buf[SARASMG_PRESSURE]));      /* p:151: whole padded box */
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+int sarasmg_solve(sarasmg_handle s, double *p_inout, const double *rhs, int *cycles_done, double *residual_history, int *coarse_iters) {
+    TRY(sarasmg_upload(s, p_inout, rhs));
+    TRY(sarasmg_solve_resident(s, cycles_done, residual_history, coarse_iters));
+    TRY(sarasmg_download(s, p_inout));
+    return 0;
+}
+
+int sarasmg_analytic_deviation(sarasmg_handle s, double *max_dev) {
+    if (!s || !max_dev) return set_err("sarasmg_analytic_deviation: null argument");
+    CU(cudaSetDevice(s->d.device));
+    return analytic_deviation(s, max_dev);
+}
+
+int sarasmg_level_dims(sarasmg_handle s, int level, int n[3], int F[3]) {
+    if (!s || level < 0 || level > s->D) return set_err("sarasmg_level_dims: bad level");
+    const LevelView &v = s->lev[level].v;
+    n[0] = v.nx; n[1] = v.ny; n[2] = v.nz; F[0] = v.Fx; F[1] = v.Fy; F[2] = v.Fz;
+    return 0;
+}
+
+int sarasmg_level_set(sarasmg_handle s, int level, int which, const double *host) {
+    if (!s || level < 0 || level > s->D || which < 0 || which > 2 || !host) return set_err("sarasmg_level_set: bad argument");
+    CU(cudaSetDevice(s->d.device));
+    TRY(copy_h2d(s, s->lev[level], s->lev[level].buf[which], host));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+int sarasmg_level_get(sarasmg_handle s, int level, int which, double *host) {
+    if (!s || level < 0 || level > s->D || which < 0 || which > 2 || !host) return set_err("sarasmg_level_get: bad argument");
+    CU(cudaSetDevice(s->d.device));
+    TRY(copy_d2h(s, s->lev[level], host, s->lev[level].buf[which]));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+int sarasmg_set_level(sarasmg_handle s, int v) {
+    if (!s || v < 0 || v > s->D) return set_err("sarasmg_set_level: bad level");
+    s->vLevel = v;
+    return 0;
+}
+int sarasmg_set_zero_bc(sarasmg_handle s, int z) {
+    if (!s) return set_err("null handle");
+    s->zeroBC = z ? 1 : 0;
+    return 0;
+}
+
+#define ENTER(s)                                         \
+    if (!(s)) return set_err("null handle");             \
+    CU(cudaSetDevice((s)->d.device));
+
+int sarasmg_op_update_pads(sarasmg_handle s, int which) {
+    ENTER(s);
+    if (which < 0 || which > 2) return set_err("bad array id");
+    TRY(update_pads(s, s->vLevel, s->lev[s->vLevel].buf[which]));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+int sarasmg_op_impose_bc(sarasmg_handle s) { ENTER(s); TRY(impose_bc(s, s->vLevel)); CU(cudaStreamSynchronize(s->st)); return 0; }
+int sarasmg_op_smooth(sarasmg_handle s, int count) { ENTER(s); TRY(op_smooth(s, count)); CU(cudaStreamSynchronize(s->st)); return 0; }
+int sarasmg_op_compute_residual(sarasmg_handle s) { ENTER(s); TRY(op_compute_residual(s)); CU(cudaStreamSynchronize(s->st)); return 0; }
+int sarasmg_op_coarsen(sarasmg_handle s) { ENTER(s); TRY(op_coarsen(s)); CU(cudaStreamSynchronize(s->st)); return 0; }
+int sarasmg_op_prolong(sarasmg_handle s) { ENTER(s); TRY(op_prolong(s)); CU(cudaStreamSynchronize(s->st)); return 0; }
+int sarasmg_op_solve_coarsest(sarasmg_handle s, int *iters) { ENTER(s); return op_solve_coarsest(s, iters, true); }
+int sarasmg_op_compute_error(sarasmg_handle s, int norm, double *value) {
+    ENTER(s);
+    if (!value) return set_err("null value");
+    return op_compute_error(s, norm, value);
+}
+int sarasmg_op_vcycle(sarasmg_handle s, int *coarse_iters) {
+    ENTER(s);
+    *s->h_iters = 0;
+    TRY(op_vcycle(s, nullptr));
+    CU(cudaStreamSynchronize(s->st));
+    s->last_coarse_iters = *s->h_iters;
+    if (coarse_iters) *coarse_iters = s->last_coarse_iters;
+    return 0;
+}
+
+/* ---- self tests ---- */
+
+/* testProlong (d3:689-719, d2:481-507): coarse level 1 filled with a linear pattern, prolonged, compared with
+ * the same pattern on level 0.  The fine array starts at 0, so "+= smoothedPres" adds nothing. */
+int sarasmg_selftest_prolong(sarasmg_handle s, double *max_err) {
+    ENTER(s);
+    if (s->D < 1) return set_err("selftest_prolong needs vc_depth >= 1");
+    std::vector<double> expect, coarse, got;
+    for (int l = 0; l <= 1; l++) {
+        const LevelView &v = s->lev[l].v;
+        std::vector<double> &A = (l == 0) ? expect : coarse;
+        A.assign((size_t)v.Fx * v.Fy * v.Fz, 0.0);
+        for (int i = 0; i < v.nx; i++) for (int j = 0; j < v.ny; j++) for (int k = 0; k < v.nz; k++) {
+            const size_t o = ((size_t)(i + 1) * v.Fy + (j + 1)) * v.Fz + (k + 1);
+            A[o] = s->planar ? (s->d.rank + 1) * 100 + i * 10 + k : (s->d.rank + 1) * 1000 + i * 100 + j * 10 + k;
+        }
+    }
+    got.assign(expect.size(), 0.0);
+    TRY(sarasmg_level_set(s, 0, SARASMG_PRESSURE, got.data()));
+    TRY(sarasmg_level_set(s, 1, SARASMG_PRESSURE, coarse.data()));
+    s->vLevel = 1;
+    TRY(op_prolong(s));
+    TRY(sarasmg_level_get(s, 0, SARASMG_PRESSURE, got.data()));
+    double m = 0.0;
+    for (size_t q = 0; q < got.size(); q++) m = std::max(m, std::fabs(got[q] - expect[q]));
+    *max_err = m;
+    return 0;
+}
+
+/* testTransfer (d3:722-777, d2:510-550): fill the core of every level with (rank+1)*1000 + 100 i + 10 j + k,
+ * run updatePads on every level and compare the x/y pads with what the neighbour must have sent.
+ * (The reference fills only level 0 and indexes one level past the hierarchy, d3:759-764; this is the test as intended.) */
+int sarasmg_selftest_transfer(sarasmg_handle s, double *max_err) {
+    ENTER(s);
+    double worst = 0.0;
+    const int *fr = s->d.face_ranks;
+    for (int l = 0; l <= s->D; l++) {
+        const LevelView &v = s->lev[l].v;
+        std::vector<double> A((size_t)v.Fx * v.Fy * v.Fz, 0.0);
+        auto at = [&](int i, int j, int k) -> double & { return A[((size_t)(i + 1) * v.Fy + (j + 1)) * v.Fz + (k + 1)]; };
+        auto val = [&](int rank, int i, int j, int k) -> double {
+            return s->planar ? (rank + 1) * 100 + i * 10 + k : (rank + 1) * 1000 + i * 100 + j * 10 + k;
+        };
+        for (int i = 0; i < v.nx; i++) for (int j = 0; j < v.ny; j++) for (int k = 0; k < v.nz; k++) at(i, j, k) = val(s->d.rank, i, j, k);
+        TRY(sarasmg_level_set(s, l, SARASMG_PRESSURE, A.data()));
+        s->vLevel = l;
+        TRY(update_pads(s, l, s->lev[l].buf[SARASMG_PRESSURE]));
+        TRY(sarasmg_level_get(s, l, SARASMG_PRESSURE, A.data()));
+        const int xE = v.nx - 1, yE = v.ny - 1;
+        for (int j = 0; j < v.ny; j++) for (int k = 0; k < v.nz; k++) {
+            if (fr[0] != SARASMG_PROC_NULL) worst = std::max(worst, std::fabs(at(-1, j, k) - val(fr[0], xE - 1, j, k)));
+            if (fr[1] != SARASMG_PROC_NULL) worst = std::max(worst, std::fabs(at(xE + 1, j, k) - val(fr[1], 1, j, k)));
+        }
+        if (!s->planar)
+            for (int i = 0; i < v.nx; i++) for (int k = 0; k < v.nz; k++) {
+                if (fr[2] != SARASMG_PROC_NULL) worst = std::max(worst, std::fabs(at(i, -1, k) - val(fr[2], i, yE - 1, k)));
+                if (fr[3] != SARASMG_PROC_NULL) worst = std::max(worst, std::fabs(at(i, yE + 1, k) - val(fr[3], i, 1, k)));
+            }
+    }
+    s->vLevel = 0;
+    *max_err = worst;
+    return 0;
+}
+
+/* testPeriodic (d3:780-857, d2:553-602): sin*cos*cos sampled on every level, imposeBC, pads compared with the
+ * analytic periodic continuation.  Coordinates are the rank's level-0 x/y/zStaggr arrays (length F_d(0), base -1). */
+int sarasmg_selftest_periodic(sarasmg_handle s, const double *xs, const double *ys, const double *zs,
+                              double x_len, double y_len, double z_len, double *max_err) {
+    ENTER(s);
+    if (!xs || !zs || (!s->planar && !ys)) return set_err("selftest_periodic: null coordinates");
+    double worst = 0.0;
+    const LevelView &v0 = s->lev[0].v;
+    const int xE0 = v0.nx - 1, yE0 = v0.ny - 1, zE0 = v0.nz - 1;
+    const double two_pi = 2.0 * M_PI;
+    auto X = [&](int i) { return xs[i + 1]; };
+    auto Y = [&](int j) { return s->planar ? 0.0 : ys[j + 1]; };
+    auto Z = [&](int k) { return zs[k + 1]; };
+    auto f = [&](double x, double y, double z) {
+        return s->planar ? std::sin(two_pi * x / x_len) * std::cos(two_pi * z / z_len)
+                         : std::sin(two_pi * x / x_len) * std::cos(two_pi * y / y_len) * std::cos(two_pi * z / z_len);
+    };
+    const int zb = s->zeroBC;
+    for (int l = 0; l <= s->D; l++) {
+        const LevelView &v = s->lev[l].v;
+        const int st = 1 << l;
+        std::vector<double> A((size_t)v.Fx * v.Fy * v.Fz, 0.0);
+        auto at = [&](int i, int j, int k) -> double & { return A[((size_t)(i + 1) * v.Fy + (j + 1)) * v.Fz + (k + 1)]; };
+        for (int i = 0; i < v.nx; i++) for (int j = 0; j < v.ny; j++) for (int k = 0; k < v.nz; k++) at(i, j, k) = f(X(i * st), Y(j * st), Z(k * st));
+        TRY(sarasmg_level_set(s, l, SARASMG_PRESSURE, A.data()));
+        s->vLevel = l;
+        s->zeroBC = 1;
+        TRY(impose_bc(s, l));
+        TRY(sarasmg_level_get(s, l, SARASMG_PRESSURE, A.data()));
+        const int xE = v.nx - 1, yE = v.ny - 1, zE = v.nz - 1;
+        if (s->d.x_per) {
+            const double xl = X(0) - (X(st) - X(0)), xr = X(xE0) + (X(xE0) - X(xE0 - st));
+            for (int j = 0; j < v.ny; j++) for (int k = 0; k < v.nz; k++) {
+                worst = std::max(worst, std::fabs(at(-1, j, k) - f(xl, Y(j * st), Z(k * st))));
+                worst = std::max(worst, std::fabs(at(xE + 1, j, k) - f(xr, Y(j * st), Z(k * st))));
+            }
+        }
+        if (!s->planar && s->d.y_per) {
+            const double yl = Y(0) - (Y(st) - Y(0)), yr = Y(yE0) + (Y(yE0) - Y(yE0 - st));
+            for (int i = 0; i < v.nx; i++) for (int k = 0; k < v.nz; k++) {
+                worst = std::max(worst, std::fabs(at(i, -1, k) - f(X(i * st), yl, Z(k * st))));
+                worst = std::max(worst, std::fabs(at(i, yE + 1, k) - f(X(i * st), yr, Z(k * st))));
+            }
+        }
+        if (s->d.z_per) {
+            const double zl = Z(0) - (Z(st) - Z(0)), zr = Z(zE0) + (Z(zE0) - Z(zE0 - st));
+            for (int i = 0; i < v.nx; i++) for (int j = 0; j < v.ny; j++) {
+                worst = std::max(worst, std::fabs(at(i, j, -1) - f(X(i * st), Y(j * st), zl)));
+                worst = std::max(worst, std::fabs(at(i, j, zE + 1) - f(X(i * st), Y(j * st), zr)));
+            }
+        }
+    }
+    s->vLevel = 0;
+    s->zeroBC = zb;
+    *max_err = worst;
+    return 0;
+}
+
+/* ---- instrumentation ---- */
+int sarasmg_timers(sarasmg_handle s, double *comp, double *tran) {
+    ENTER(s);
+    TRY(prof_fold(s));
+    if (comp) *comp = s->t_comp;
+    if (tran) *tran = s->t_tran;
+    return 0;
+}
+long long sarasmg_kernel_launches(sarasmg_handle s) { return s ? s->launches : 0; }
+int sarasmg_reset_counters(sarasmg_handle s) {
+    ENTER(s);
+    TRY(prof_fold(s));
+    s->launches = 0;
+    memset(s->prof_ms, 0, sizeof(s->prof_ms));
+    memset(s->prof_n, 0, sizeof(s->prof_n));
+    s->t_comp = s->t_tran = 0.0;
+    return 0;
+}
+int sarasmg_profile_query(sarasmg_handle s, int kind, int level, double *total_ms, long long *launches) {
+    ENTER(s);
+    if (kind < 0 || kind >= SARASMG_K_COUNT || level < 0 || level > s->D || level >= 32) return set_err("bad kind/level");
+    TRY(prof_fold(s));
+    if (total_ms) *total_ms = s->prof_ms[kind][level];
+    if (launches) *launches = s->prof_n[kind][level];
+    return 0;
+}
+int sarasmg_last_solve_ms(sarasmg_handle s, double *ms) {
+    if (!s || !ms) return set_err("null argument");
+    *ms = s->last_solve_ms;
+    return 0;
+}
+int sarasmg_synchronize(sarasmg_handle s) { ENTER(s); CU(cudaStreamSynchronize(s->st)); return 0; }
+
+}  /* extern "C" */

@@ -1,0 +1,227 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on identical
+seeded inputs.  Bar: bit-exact for every operator whose arithmetic is order-defined (smoother,
+residual, restriction, prolongation, BCs, halos, coarse solve incl. iteration counts, V-cycle);
+reductions (norms, mean) within 1e-13 relative because their summation order differs."""
+import numpy as np
+import pytest
+
+from oracle import mgoracle as mo
+from oracle.mgoracle import Oracle
+from saras_b200 import capi
+from tests.helpers import make_solver, seeded_field, smooth_rhs, max_abs, rel_linf
+
+pytestmark = pytest.mark.gpu
+
+CASES_3D = [
+    dict(name="uuu_nnn", dim=3, xInd=4, yInd=4, zInd=4, vcDepth=2),
+    dict(name="aniso_sizes", dim=3, xInd=4, yInd=5, zInd=3, vcDepth=2),
+    dict(name="tanh_all", dim=3, xInd=4, yInd=4, zInd=5, vcDepth=3, xGrid=2, yGrid=2, zGrid=2, betaX=1.1, betaY=1.3, betaZ=1.7, Lx=2.0, Ly=1.0, Lz=1.5),
+    dict(name="ppp", dim=3, xInd=4, yInd=4, zInd=4, vcDepth=2, xPer=1, yPer=1, zPer=1),
+    dict(name="ppn_tanhz", dim=3, xInd=5, yInd=4, zInd=4, vcDepth=3, xPer=1, yPer=1, zPer=0, zGrid=2, betaZ=1.5),
+    dict(name="testpoisson", dim=3, xInd=4, yInd=4, zInd=4, vcDepth=2, test_poisson=1),
+]
+CASES_2D = [
+    dict(name="d2_nn", dim=2, xInd=5, zInd=4, vcDepth=3),
+    dict(name="d2_pp_tanh", dim=2, xInd=4, zInd=6, vcDepth=3, xPer=1, zPer=1, zGrid=2, betaZ=1.4),
+    dict(name="d2_testpoisson", dim=2, xInd=5, zInd=5, vcDepth=3, test_poisson=1),
+]
+ALL = CASES_3D + CASES_2D
+
+
+def _mk(case, **kw):
+    cfg = {k: v for k, v in case.items() if k != "name"}
+    cfg.update(kw)
+    o = Oracle(**cfg)
+    return o, make_solver(o)
+
+
+def _load_both(o, s, level, which, arr):
+    o.array(0, level, which)[...] = arr
+    s.level_set(level, which, arr)
+
+
+@pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
+@pytest.mark.parametrize("gs", [0, 1], ids=["jacobi", "gs"])
+def test_smooth_bitexact(case, gs):
+    o, s = _mk(case, gsSmooth=gs)
+    for level in range(o.depth + 1):
+        _, F = o.level_dims(level)
+        zero_bc = 1 if level > 0 else 0
+        _load_both(o, s, level, mo.PRESSURE, seeded_field(F, 10 + level))
+        _load_both(o, s, level, mo.RESIDUAL, seeded_field(F, 20 + level, 5.0))
+        for count in (1, 2, 3):
+            o.set_level(level); o.set_zero_bc(zero_bc); o.smooth(count)
+            s.set_level(level); s.set_zero_bc(zero_bc); s.smooth(count)
+            ref = o.array(0, level, mo.PRESSURE)
+            got = s.level_get(level, capi.PRESSURE)
+            assert np.array_equal(got, ref), "level %d count %d max diff %g" % (level, count, max_abs(got - ref))
+    s.close()
+
+
+@pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
+def test_residual_coarsen_prolong_bitexact(case):
+    o, s = _mk(case)
+    for level in range(o.depth):
+        _, F = o.level_dims(level)
+        _load_both(o, s, level, mo.PRESSURE, seeded_field(F, 30 + level))
+        _load_both(o, s, level, mo.RESIDUAL, seeded_field(F, 40 + level, 3.0))
+        # dirty tmp pads: the operator has to clear them (d3:91)
+        _load_both(o, s, level, mo.TMP, seeded_field(F, 50 + level))
+        o.set_level(level); o.compute_residual()
+        s.set_level(level); s.compute_residual()
+        assert np.array_equal(s.level_get(level, capi.TMP), o.array(0, level, mo.TMP))
+        o.coarsen(); s.coarsen()
+        assert np.array_equal(s.level_get(level + 1, capi.RESIDUAL), o.array(0, level + 1, mo.RESIDUAL))
+        # prolong + "+= smoothedPres": oracle needs smoothedPres = current fine pressure
+        _, Fc = o.level_dims(level + 1)
+        _load_both(o, s, level + 1, mo.PRESSURE, seeded_field(Fc, 60 + level))
+        o.array(0, level, mo.SMOOTHED)[...] = o.array(0, level, mo.PRESSURE)
+        o.prolong()
+        o.array(0, level, mo.PRESSURE)[...] += o.array(0, level, mo.SMOOTHED)
+        s.prolong()
+        got, ref = s.level_get(level, capi.PRESSURE), o.array(0, level, mo.PRESSURE)
+        assert np.array_equal(got, ref), max_abs(got - ref)
+    s.close()
+
+
+@pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
+def test_impose_bc_and_pads_bitexact(case):
+    o, s = _mk(case)
+    for level in range(o.depth + 1):
+        _, F = o.level_dims(level)
+        for zero_bc in ((0, 1) if level == 0 else (1,)):
+            _load_both(o, s, level, mo.PRESSURE, seeded_field(F, 70 + level))
+            o.set_level(level); o.set_zero_bc(zero_bc); o.impose_bc()
+            s.set_level(level); s.set_zero_bc(zero_bc); s.impose_bc()
+            assert np.array_equal(s.level_get(level, capi.PRESSURE), o.array(0, level, mo.PRESSURE))
+        _load_both(o, s, level, mo.TMP, seeded_field(F, 80 + level))
+        o.update_pads(mo.TMP); s.update_pads(capi.TMP)
+        assert np.array_equal(s.level_get(level, capi.TMP), o.array(0, level, mo.TMP))
+    s.close()
+
+
+@pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
+def test_solve_coarsest_bitexact(case):
+    o, s = _mk(case, mgTolerance=1e-7)
+    level = o.depth
+    _, F = o.level_dims(level)
+    rhs = seeded_field(F, 90, 0.01)
+    rhs[...] -= rhs.mean()
+    _load_both(o, s, level, mo.RESIDUAL, rhs)
+    _load_both(o, s, level, mo.PRESSURE, np.zeros(F))
+    o.set_level(level); o.set_zero_bc(1)
+    s.set_level(level); s.set_zero_bc(1)
+    it_ref = o.solve_coarsest()
+    it_got = s.solve_coarsest()
+    assert it_got == it_ref
+    assert np.array_equal(s.level_get(level, capi.PRESSURE), o.array(0, level, mo.PRESSURE))
+    s.close()
+
+
+@pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
+@pytest.mark.parametrize("norm", [1, 2])
+def test_compute_error(case, norm):
+    o, s = _mk(case)
+    _, F = o.level_dims(0)
+    _load_both(o, s, 0, mo.PRESSURE, seeded_field(F, 100))
+    _load_both(o, s, 0, mo.RESIDUAL, seeded_field(F, 101, 2.0))
+    o.set_level(0); s.set_level(0)
+    ref = o.compute_error(norm)
+    got = s.compute_error(norm)
+    if norm == 1:
+        assert got == ref          # max-norms are order independent -> bit-exact
+    else:
+        assert abs(got - ref) <= 1e-13 * abs(ref)
+    s.close()
+
+
+@pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
+@pytest.mark.parametrize("gs", [0, 1], ids=["jacobi", "gs"])
+def test_vcycle_bitexact(case, gs):
+    o, s = _mk(case, gsSmooth=gs)
+    _, F = o.level_dims(0)
+    rhs = smooth_rhs(o, 0, F) if not case.get("test_poisson") else np.ones(F)
+    _load_both(o, s, 0, mo.RESIDUAL, rhs)
+    _load_both(o, s, 0, mo.PRESSURE, seeded_field(F, 110, 0.1))
+    for cyc in range(2):
+        o.vcycle()
+        it = s.vcycle()
+        got, ref = s.level_get(0, capi.PRESSURE), o.array(0, 0, mo.PRESSURE)
+        assert np.array_equal(got, ref), "cycle %d: max diff %g" % (cyc, max_abs(got - ref))
+    s.close()
+
+
+MGSOLVE_CASES = [
+    # C1 mgTest shape at reduced size: TEST_POISSON, rhs = 1, Dirichlet r^2/6, GS, resType 2, all cycles run
+    dict(name="mgtest_33_gs", dim=3, test_poisson=1, xInd=5, yInd=5, zInd=5, vcDepth=3, vcCount=12, gsSmooth=1, resType=2),
+    dict(name="mgtest_33_jacobi", dim=3, test_poisson=1, xInd=5, yInd=5, zInd=5, vcDepth=3, vcCount=12, gsSmooth=0, resType=2),
+    # production mode: Neumann, mean removal, stagnation break
+    dict(name="neumann_33_jacobi", dim=3, xInd=5, yInd=5, zInd=5, vcDepth=3, vcCount=20, gsSmooth=0, resType=1, mgTolerance=1e-6),
+    dict(name="neumann_tanh_gs", dim=3, xInd=5, yInd=4, zInd=5, vcDepth=3, vcCount=20, gsSmooth=1, resType=2, mgTolerance=1e-7,
+         zGrid=2, betaZ=1.3, preSmooth=3, postSmooth=1),
+    dict(name="ppp_33_gs_v44", dim=3, xInd=5, yInd=5, zInd=5, vcDepth=3, vcCount=5, gsSmooth=1, resType=1, xPer=1, yPer=1, zPer=1,
+         preSmooth=4, postSmooth=4),
+    dict(name="restype0_one_cycle", dim=3, xInd=4, yInd=4, zInd=4, vcDepth=2, vcCount=7, gsSmooth=0, resType=0),
+    # C2 LDC shape: 2-D, GS, resType 1, depth 4, 7 cycles
+    dict(name="ldc2d_129", dim=2, xInd=7, zInd=7, vcDepth=4, vcCount=7, gsSmooth=1, resType=1),
+    dict(name="d2_testpoisson_65", dim=2, test_poisson=1, xInd=6, zInd=6, vcDepth=4, vcCount=10, gsSmooth=1, resType=2),
+    dict(name="d2_periodic_jacobi", dim=2, xInd=6, zInd=5, vcDepth=3, vcCount=10, gsSmooth=0, resType=2, xPer=1, zPer=1),
+]
+
+
+@pytest.mark.parametrize("case", MGSOLVE_CASES, ids=lambda c: c["name"])
+def test_mg_solve_parity(case):
+    """north_star bar: identical V-cycle count, per-cycle residuals within 1e-10 relative, final pressure within
+    1e-12 relative L-inf.  TEST_POISSON cases (no mean removal) are additionally bit-exact in the field."""
+    o, s = _mk(case)
+    _, F = o.level_dims(0)
+    if case.get("test_poisson"):
+        rhs = np.ones(F)
+        p0 = np.zeros(F)
+    else:
+        rhs = smooth_rhs(o, 0, F) + 0.3        # non-zero mean: exercises the mean removal
+        p0 = seeded_field(F, 7, 0.01)
+    p_ref = p0.copy()
+    ref = o.mg_solve([p_ref], [rhs.copy()])
+    p_got = p0.copy()
+    got = s.mg_solve(p_got, rhs.copy())
+    assert got["cycles"] == ref["cycles"]
+    assert np.array_equal(got["coarse_iters"], ref["coarse_iters"])
+    for a, b in zip(got["residuals"], ref["residuals"]):
+        assert abs(a - b) <= 1e-10 * abs(b) + 1e-300
+    assert rel_linf(p_got, p_ref) <= 1e-12
+    if case.get("test_poisson"):
+        assert np.array_equal(p_got, p_ref)
+        assert abs(s.analytic_deviation() - ref["max_dev"]) <= 1e-15
+    s.close()
+
+
+def test_selftests():
+    """the reference's own known-answer self tests (poisson_d3.cc:689-857), tolerance 1e-10 as in poisson_test.cc:74-97"""
+    o = Oracle(dim=3, xInd=4, yInd=4, zInd=4, vcDepth=2, xPer=1, yPer=1, zPer=1, wall_null=0)
+    s = make_solver(o)
+    assert s.selftest_prolong() <= 1e-10
+    assert s.selftest_transfer() <= 1e-10
+    assert s.selftest_periodic(o.staggr(0, 0), o.staggr(0, 1), o.staggr(0, 2), 1.0, 1.0, 1.0) <= 1e-10
+    s.close()
+    o = Oracle(dim=2, xInd=5, zInd=5, vcDepth=3, xPer=1, zPer=1, wall_null=0)
+    s = make_solver(o)
+    assert s.selftest_prolong() <= 1e-10
+    assert s.selftest_transfer() <= 1e-10
+    assert s.selftest_periodic(o.staggr(0, 0), None, o.staggr(0, 2), 1.0, 1.0, 1.0) <= 1e-10
+    s.close()
+
+
+def test_persistent_hierarchy_repeat_solves():
+    """the device hierarchy persists across time steps and carries no numerical state between calls (poisson.cc:107-111)"""
+    o = Oracle(dim=3, xInd=4, yInd=4, zInd=4, vcDepth=2, vcCount=6, gsSmooth=0, resType=2, preSmooth=3, postSmooth=3)
+    s = make_solver(o)
+    _, F = o.level_dims(0)
+    rhs = smooth_rhs(o, 0, F)
+    outs = []
+    for rep in range(3):
+        p = np.zeros(F)
+        s.mg_solve(p, rhs)
+        outs.append(p)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
+    s.close()
