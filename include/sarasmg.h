@@ -141,6 +141,11 @@ enum { SARASMG_K_SMOOTH = 0, SARASMG_K_RESIDUAL, SARASMG_K_COARSEN, SARASMG_K_PR
 int sarasmg_profile_query(sarasmg_handle h, int kind, int level, double *total_ms, long long *launches);
 /* device-side time of the last sarasmg_solve_resident / sarasmg_solve V-cycle loop (CUDA events), ms */
 int sarasmg_last_solve_ms(sarasmg_handle h, double *ms);
+/* TEST HOOK.  mgSolve subtracts globalAvg = mean of the padded RHS (poisson.cc:122-128).  The reference forms that mean
+ * with one sequential sum whose rounding error (~1e-14 relative) no parallel reduction reproduces, and the singular
+ * Neumann/periodic solve amplifies it ~100x.  With enable != 0 the solver subtracts `value` instead, so a test can feed
+ * the oracle's mean and then require bit-exact fields in production mode as well. */
+int sarasmg_debug_set_rhs_mean(sarasmg_handle h, int enable, double value);
 /* blocks until all work of the handle has finished */
 int sarasmg_synchronize(sarasmg_handle h);
 

@@ -43,6 +43,7 @@ struct mgo_solver {
     double dXi, dEt, dZt, xLen, yLen, zLen;
     rank_state *rk;
     double lups;
+    double lastGlobalAvg;
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -324,6 +325,7 @@ void mgo_set_level(mgo_solver *s, int v) { s->vLevel = v; }
 int mgo_get_level(const mgo_solver *s) { return s->vLevel; }
 void mgo_set_zero_bc(mgo_solver *s, int z) { s->zeroBC = z; }
 double mgo_lup_count(const mgo_solver *s) { return s->lups; }
+double mgo_last_global_avg(const mgo_solver *s) { return s->lastGlobalAvg; }
 void mgo_lup_reset(mgo_solver *s) { s->lups = 0.0; }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -922,6 +924,7 @@ int mgo_mg_solve(mgo_solver *s, double *const *p_inout, const double *const *rhs
             globalAvg += localMean;                         /* MPI_SUM in rank order */
         }
         globalAvg /= s->nProc;
+        s->lastGlobalAvg = globalAvg;
         for (int r = 0; r < s->nProc; r++) {
             double *Rh = s->rk[r].arr[MGO_RESIDUAL][0];
             for (size_t q = 0; q < L0->size; q++) Rh[q] -= globalAvg;

@@ -106,6 +106,8 @@ double mgo_test_periodic(mgo_solver *s);
 /* LUP counters since creation/reset: smoother + residual + error-norm stencil evaluations */
 double mgo_lup_count(const mgo_solver *s);
 void mgo_lup_reset(mgo_solver *s);
+/* globalAvg subtracted from the RHS by the last mgo_mg_solve (poisson.cc:122-128) */
+double mgo_last_global_avg(const mgo_solver *s);
 
 #ifdef __cplusplus
 }

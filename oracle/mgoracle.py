@@ -82,6 +82,8 @@ def _load(fast=False):
     lib.mgo_test_prolong.restype = C.c_double
     lib.mgo_test_prolong.argtypes = [vp]
     lib.mgo_lup_count.restype = C.c_double
+    lib.mgo_last_global_avg.restype = C.c_double
+    lib.mgo_last_global_avg.argtypes = [vp]
     lib.mgo_lup_count.argtypes = [vp]
     _LIBS[key] = lib
     return lib
@@ -215,6 +217,9 @@ class Oracle:
 
     def lups(self):
         return self.lib.mgo_lup_count(self.h)
+
+    def last_global_avg(self):
+        return self.lib.mgo_last_global_avg(self.h)
 
     def lup_reset(self):
         self.lib.mgo_lup_reset(self.h)

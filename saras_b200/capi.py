@@ -49,7 +49,7 @@ SYMBOLS = [
     "sarasmg_op_coarsen", "sarasmg_op_prolong", "sarasmg_op_solve_coarsest", "sarasmg_op_compute_error", "sarasmg_op_vcycle",
     "sarasmg_selftest_prolong", "sarasmg_selftest_transfer", "sarasmg_selftest_periodic",
     "sarasmg_timers", "sarasmg_kernel_launches", "sarasmg_reset_counters", "sarasmg_profile_query",
-    "sarasmg_last_solve_ms", "sarasmg_synchronize",
+    "sarasmg_last_solve_ms", "sarasmg_synchronize", "sarasmg_debug_set_rhs_mean",
 ]
 
 
@@ -92,6 +92,7 @@ def load():
     lib.sarasmg_kernel_launches.argtypes = [vp]
     lib.sarasmg_profile_query.argtypes = [vp, C.c_int, C.c_int, _dp, C.POINTER(C.c_longlong)]
     lib.sarasmg_last_solve_ms.argtypes = [vp, _dp]
+    lib.sarasmg_debug_set_rhs_mean.argtypes = [vp, C.c_int, C.c_double]
     _lib = lib
     return lib
 
@@ -308,6 +309,9 @@ class Solver:
         v = C.c_double(0.0)
         self._check(self.lib.sarasmg_last_solve_ms(self.h, C.byref(v)))
         return v.value
+
+    def debug_set_rhs_mean(self, enable, value=0.0):
+        self._check(self.lib.sarasmg_debug_set_rhs_mean(self.h, int(enable), float(value)))
 
     def synchronize(self):
         self._check(self.lib.sarasmg_synchronize(self.h))

@@ -97,6 +97,8 @@ struct sarasmg_solver_s {
     cudaEvent_t ev_solve0, ev_solve1;
     double last_solve_ms;
     int last_coarse_iters;
+    int mean_override;          /* test hook: use mean_value instead of the device-computed RHS mean */
+    double mean_value;
 };
 
 typedef sarasmg_solver_s S;
@@ -625,6 +627,7 @@ static int solve_core(S *s, const double *in_p, const double *in_rhs, int *cycle
         double globalAvg = 0.0;
         for (int r = 0; r < d.n_proc; r++) globalAvg += sums[r] / cnt;      /* sum of local means, rank order */
         globalAvg /= d.n_proc;
+        if (s->mean_override) globalAvg = s->mean_value;
         k_sub_scalar_padded<<<nbp, 256, 0, s->st>>>(L0.buf[SARASMG_RESIDUAL], L0.v, globalAvg);
         TRY(kcheck(s, "k_sub_scalar_padded"));
     }
@@ -719,6 +722,7 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     s->launches = 0;
     s->t_comp = s->t_tran = 0.0; s->bucket = 0;
     s->last_solve_ms = 0.0; s->last_coarse_iters = 0;
+    s->mean_override = 0; s->mean_value = 0.0;
     memset(s->prof_ms, 0, sizeof(s->prof_ms));
     memset(s->prof_n, 0, sizeof(s->prof_n));
     for (int q = 0; q < 3; q++) s->d_wall[q] = nullptr;
@@ -959,8 +963,11 @@ int sarasmg_op_vcycle(sarasmg_handle s, int *coarse_iters) {
 
 /* ---- self tests ---- */
 
-/* testProlong (d3:689-719, d2:481-507): coarse level 1 filled with a linear pattern, prolonged, compared with
- * the same pattern on level 0.  The fine array starts at 0, so "+= smoothedPres" adds nothing. */
+/* testProlong (d3:689-719, d2:481-507): level 1 holds the linear pattern (rank+1)*1000 + 100 i + 10 j + k sampled at the
+ * even fine points, it is prolonged and compared with the same pattern on level 0 (trilinear interpolation is exact for
+ * linear data).  The reference's version is stale: it fills the coarse level with COARSE indices and then indexes
+ * residualData(vLevel - 1) = residualData(-1) (d3:716); this is the test as intended.  The fine array starts at 0, so
+ * the fused "+= smoothedPres" adds nothing. */
 int sarasmg_selftest_prolong(sarasmg_handle s, double *max_err) {
     ENTER(s);
     if (s->D < 1) return set_err("selftest_prolong needs vc_depth >= 1");
@@ -971,7 +978,9 @@ int sarasmg_selftest_prolong(sarasmg_handle s, double *max_err) {
         A.assign((size_t)v.Fx * v.Fy * v.Fz, 0.0);
         for (int i = 0; i < v.nx; i++) for (int j = 0; j < v.ny; j++) for (int k = 0; k < v.nz; k++) {
             const size_t o = ((size_t)(i + 1) * v.Fy + (j + 1)) * v.Fz + (k + 1);
-            A[o] = s->planar ? (s->d.rank + 1) * 100 + i * 10 + k : (s->d.rank + 1) * 1000 + i * 100 + j * 10 + k;
+            const int st = 1 << l;      /* level-1 point (i,j,k) is fine point (2i,2j,2k) */
+            A[o] = s->planar ? (s->d.rank + 1) * 100 + i * st * 10 + k * st
+                             : (s->d.rank + 1) * 1000 + i * st * 100 + j * st * 10 + k * st;
         }
     }
     got.assign(expect.size(), 0.0);
@@ -1108,6 +1117,12 @@ int sarasmg_profile_query(sarasmg_handle s, int kind, int level, double *total_m
 int sarasmg_last_solve_ms(sarasmg_handle s, double *ms) {
     if (!s || !ms) return set_err("null argument");
     *ms = s->last_solve_ms;
+    return 0;
+}
+int sarasmg_debug_set_rhs_mean(sarasmg_handle s, int enable, double value) {
+    if (!s) return set_err("null handle");
+    s->mean_override = enable ? 1 : 0;
+    s->mean_value = value;
     return 0;
 }
 int sarasmg_synchronize(sarasmg_handle s) { ENTER(s); CU(cudaStreamSynchronize(s->st)); return 0; }
