@@ -77,6 +77,8 @@ typedef struct {
 const char *sarasmg_last_error(void);
 int sarasmg_version(void);
 
+/* number of usable CUDA devices (0 and an error when there is none) */
+int sarasmg_device_count(int *count);
 /* fills out[SARASMG_UNIQUE_ID_BYTES] with a fresh ncclUniqueId */
 int sarasmg_get_unique_id(void *out);
 

@@ -4,6 +4,6 @@ The product is the CUDA library behind include/sarasmg.h plus the C++ drop-in fo
 `poisson` / `multigrid_d2` / `multigrid_d3` classes under saras_b200/host/.  This Python package is
 plumbing for tests and bench.py (ctypes over the same C-ABI).
 """
-from . import capi  # noqa: F401
+from . import capi, host_api  # noqa: F401
 
-__all__ = ["capi"]
+__all__ = ["capi", "host_api"]

@@ -42,7 +42,7 @@ class Desc(C.Structure):
 _lib = None
 
 SYMBOLS = [
-    "sarasmg_last_error", "sarasmg_version", "sarasmg_get_unique_id", "sarasmg_create", "sarasmg_destroy",
+    "sarasmg_last_error", "sarasmg_version", "sarasmg_device_count", "sarasmg_get_unique_id", "sarasmg_create", "sarasmg_destroy",
     "sarasmg_solve", "sarasmg_upload", "sarasmg_solve_resident", "sarasmg_download", "sarasmg_analytic_deviation",
     "sarasmg_level_dims", "sarasmg_level_set", "sarasmg_level_get", "sarasmg_set_level", "sarasmg_set_zero_bc",
     "sarasmg_op_update_pads", "sarasmg_op_impose_bc", "sarasmg_op_smooth", "sarasmg_op_compute_residual",
@@ -64,6 +64,7 @@ def load():
     vp, ip = C.c_void_p, C.POINTER(C.c_int)
     lib.sarasmg_last_error.restype = C.c_char_p
     lib.sarasmg_get_unique_id.argtypes = [C.c_void_p]
+    lib.sarasmg_device_count.argtypes = [C.POINTER(C.c_int)]
     lib.sarasmg_create.argtypes = [C.POINTER(Desc), C.POINTER(vp)]
     lib.sarasmg_destroy.argtypes = [vp]
     lib.sarasmg_solve.argtypes = [vp, _dp, _dp, ip, _dp, ip]
@@ -117,6 +118,16 @@ class Solver:
       walls, rank topology.  See include/sarasmg.h.
     """
 
+    @classmethod
+    def from_handle(cls, handle, dim, vc_depth, vc_count):
+        """Non-owning view of a sarasmg_handle created elsewhere (the C++ drop-in's nativeHandle())."""
+        self = cls.__new__(cls)
+        self.lib = load()
+        self.h = C.c_void_p(handle)
+        self.dim, self.depth, self.vc_count = dim, vc_depth, vc_count
+        self._owned = False
+        return self
+
     def __init__(self, *, dim, vc_depth, vc_count, pre_smooth, post_smooth, gs_smooth, res_type, mg_tolerance,
                  x_per, y_per, z_per, n0, coefs, metrics, walls=None, test_poisson=0, print_residual=0,
                  rank=0, n_proc=1, npx=1, npy=1, x_rank=0, y_rank=0, face_ranks=(PROC_NULL,) * 4,
@@ -161,6 +172,7 @@ class Solver:
         self.desc = d
         self.dim, self.depth, self.vc_count = dim, vc_depth, vc_count
         self.h = C.c_void_p()
+        self._owned = True
         self._check(self.lib.sarasmg_create(C.byref(d), C.byref(self.h)))
 
     # -- plumbing --------------------------------------------------------------------------------
@@ -170,7 +182,8 @@ class Solver:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.sarasmg_destroy(self.h)
+            if getattr(self, "_owned", True):
+                self.lib.sarasmg_destroy(self.h)
             self.h = None
 
     def __del__(self):

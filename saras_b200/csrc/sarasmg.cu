@@ -693,6 +693,15 @@ extern "C" {
 const char *sarasmg_last_error(void) { return g_err.c_str(); }
 int sarasmg_version(void) { return 100; }
 
+int sarasmg_device_count(int *count) {
+    if (!count) return set_err("null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return set_err("cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = n;
+    return 0;
+}
+
 int sarasmg_get_unique_id(void *out) {
     static_assert(sizeof(ncclUniqueId) == SARASMG_UNIQUE_ID_BYTES, "ncclUniqueId size");
     ncclUniqueId id;
