@@ -143,6 +143,17 @@ enum { SARASMG_K_SMOOTH = 0, SARASMG_K_RESIDUAL, SARASMG_K_COARSEN, SARASMG_K_PR
 int sarasmg_profile_query(sarasmg_handle h, int kind, int level, double *total_ms, long long *launches);
 /* device-side time of the last sarasmg_solve_resident / sarasmg_solve V-cycle loop (CUDA events), ms */
 int sarasmg_last_solve_ms(sarasmg_handle h, double *ms);
+/* with SARASMG_FLAG_PROFILE: only operators on levels <= max_level are bracketed with events (default: all levels).
+ * Lets a benchmark time the bandwidth-bound fine levels live without adding host work to the latency-bound coarse ones. */
+int sarasmg_set_profile_max_level(sarasmg_handle h, int max_level);
+/* user timing events on the SOLVER's stream (the stream every kernel of the handle is launched on): record slot 0..7,
+ * then elapsed(a, b) synchronises on b and returns the device time between the two records in ms */
+int sarasmg_event_record(sarasmg_handle h, int slot);
+int sarasmg_event_elapsed_ms(sarasmg_handle h, int slot_a, int slot_b, double *ms);
+/* page-lock a caller-owned host range (the Blitz storage of Pp / mgRHS, which SARAS allocates once and reuses every
+ * time step) so that the copies of sarasmg_solve run at PCIe speed.  sarasmg_solve does this by itself the first time it
+ * sees a pointer unless SARASMG_NO_PIN is set in the environment; ranges are released by sarasmg_destroy. */
+int sarasmg_host_register(sarasmg_handle h, const void *ptr, unsigned long long bytes);
 /* TEST HOOK.  mgSolve subtracts globalAvg = mean of the padded RHS (poisson.cc:122-128).  The reference forms that mean
  * with one sequential sum whose rounding error (~1e-14 relative) no parallel reduction reproduces, and the singular
  * Neumann/periodic solve amplifies it ~100x.  With enable != 0 the solver subtracts `value` instead, so a test can feed

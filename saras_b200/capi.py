@@ -50,6 +50,7 @@ SYMBOLS = [
     "sarasmg_selftest_prolong", "sarasmg_selftest_transfer", "sarasmg_selftest_periodic",
     "sarasmg_timers", "sarasmg_kernel_launches", "sarasmg_reset_counters", "sarasmg_profile_query",
     "sarasmg_last_solve_ms", "sarasmg_synchronize", "sarasmg_debug_set_rhs_mean",
+    "sarasmg_set_profile_max_level", "sarasmg_event_record", "sarasmg_event_elapsed_ms", "sarasmg_host_register",
 ]
 
 
@@ -94,6 +95,10 @@ def load():
     lib.sarasmg_profile_query.argtypes = [vp, C.c_int, C.c_int, _dp, C.POINTER(C.c_longlong)]
     lib.sarasmg_last_solve_ms.argtypes = [vp, _dp]
     lib.sarasmg_debug_set_rhs_mean.argtypes = [vp, C.c_int, C.c_double]
+    lib.sarasmg_set_profile_max_level.argtypes = [vp, C.c_int]
+    lib.sarasmg_event_record.argtypes = [vp, C.c_int]
+    lib.sarasmg_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, _dp]
+    lib.sarasmg_host_register.argtypes = [vp, C.c_void_p, C.c_ulonglong]
     _lib = lib
     return lib
 
@@ -328,6 +333,20 @@ class Solver:
 
     def synchronize(self):
         self._check(self.lib.sarasmg_synchronize(self.h))
+
+    def set_profile_max_level(self, level):
+        self._check(self.lib.sarasmg_set_profile_max_level(self.h, int(level)))
+
+    def event_record(self, slot):
+        self._check(self.lib.sarasmg_event_record(self.h, int(slot)))
+
+    def event_elapsed_ms(self, a, b):
+        v = C.c_double(0.0)
+        self._check(self.lib.sarasmg_event_elapsed_ms(self.h, int(a), int(b), C.byref(v)))
+        return v.value
+
+    def host_register(self, arr):
+        self._check(self.lib.sarasmg_host_register(self.h, C.c_void_p(arr.ctypes.data), arr.nbytes))
 
 
 def get_unique_id():

@@ -38,6 +38,36 @@ __host__ __device__ __forceinline__ long long mg_at(const LevelView &L, int i, i
 enum { FACE_NONE = 0, FACE_MIRROR = 1, FACE_NEG_MIRROR = 2, FACE_WALL = 3, FACE_PERIODIC = 4, FACE_ZERO = 5 };
 
 /* ------------------------------------------------------------------------------------------------ */
+/* exact division by a loop-invariant divisor                                                         */
+/* The reference divides by hx*hx, 2.0*hx, ... (6 divisions per residual point) and by the stencil     */
+/* diagonal (1 per smoother point).  An IEEE fp64 division is ~12 dependent fp64-pipe instructions on  */
+/* the GPU, which makes the residual compute-bound instead of HBM-bound.  When the divisor b does not  */
+/* change along a thread's march, y = RN(1/b) is formed ONCE with a true IEEE division and every       */
+/* quotient is then recovered exactly:  q0 = RN(a*y) is within 2 ulp of a/b, r = fma(-b, q0, a) is      */
+/* exact, q1 = RN(q0 + r*y) is a faithful rounding of a/b, and one more step from a faithful quotient   */
+/* with y = RN(1/b) returns RN(a/b) (Markstein 1990; Muller et al., Handbook of Floating-Point          */
+/* Arithmetic, "division with an FMA").  The fused operations here do not contract any product of the   */
+/* reference's expressions: they only rebuild the correctly rounded quotient the `/` would give, so     */
+/* the result is bit-identical.  Exactness of r needs a*2^-106 to stay normal and a*y not to overflow:  */
+/* operands outside 2^-823 <= |a| <= 2^777 take the IEEE division (a == 0 yields 0 on either path).     */
+/* ------------------------------------------------------------------------------------------------ */
+/* out of line on purpose: inlined, the compiler hoists the whole IEEE division sequence above the branch */
+__device__ __noinline__ double div_ieee(const double a, const double b) { return a / b; }
+__device__ __forceinline__ double div_inv(const double a, const double b, const double y) {
+    double q = a * y;
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    const unsigned hi = (unsigned)__double2hiint(a);
+    const unsigned e = (hi >> 20) & 0x7ffu;
+    if ((e - 200u) > 1600u) {                                       /* rare: tiny, huge, zero, inf, nan */
+        if (((hi << 1) | (unsigned)__double2loint(a)) != 0u) q = div_ieee(a, b);
+    }
+    return q;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* point formulas                                                                                    */
 /* ------------------------------------------------------------------------------------------------ */
 
@@ -55,6 +85,19 @@ __device__ __forceinline__ double relax3(double pE, double pW, double pN, double
     t = t - two_hxhyhz * rhs;
     return t / den;
 }
+/* the numerator of relax3 alone (same association) */
+__device__ __forceinline__ double relax3_num(double pE, double pW, double pN, double pS, double pT, double pB, double rhs,
+                                             double cx2, double cx1, double hx, double cy2, double cy1, double hy,
+                                             double cz2, double cz1, double hz, double two_hxhyhz) {
+    double t = cx2 * (pE + pW) * 2.0;
+    t = t + cx1 * (pE - pW) * hx;
+    t = t + cy2 * (pN + pS) * 2.0;
+    t = t + cy1 * (pN - pS) * hy;
+    t = t + cz2 * (pT + pB) * 2.0;
+    t = t + cz1 * (pT - pB) * hz;
+    t = t - two_hxhyhz * rhs;
+    return t;
+}
 
 /* d2:121-126 / 133-138 / 160-165;  den = 4.0*(cx2 + cz2) */
 __device__ __forceinline__ double relax2(double pE, double pW, double pT, double pB, double rhs,
@@ -67,6 +110,16 @@ __device__ __forceinline__ double relax2(double pE, double pW, double pT, double
     t = t - two_hzhx * rhs;
     return t / den;
 }
+__device__ __forceinline__ double relax2_num(double pE, double pW, double pT, double pB, double rhs,
+                                             double cx2, double cx1, double hx, double cz2, double cz1, double hz,
+                                             double two_hzhx) {
+    double t = cx2 * (pE + pW) * 2.0;
+    t = t + cx1 * (pE - pW) * hx;
+    t = t + cz2 * (pT + pB) * 2.0;
+    t = t + cz1 * (pT - pB) * hz;
+    t = t - two_hzhx * rhs;
+    return t;
+}
 
 /* the Laplacian bracket of d3:100-105 / 219-224 / 411-416.  dxx = hx*hx, dx = 2.0*hx, ... */
 __device__ __forceinline__ double lap3(double pC, double pE, double pW, double pN, double pS, double pT, double pB,
@@ -78,6 +131,34 @@ __device__ __forceinline__ double lap3(double pC, double pE, double pW, double p
     t = t + y1 * (pN - pS) / dy;
     t = t + z2 * (pT - 2.0 * pC + pB) / dzz;
     t = t + z1 * (pT - pB) / dz;
+    return t;
+}
+
+/* same bracket with the six divisors' reciprocals hoisted (div_inv): bit-identical to lap3 */
+struct LapDiv { double dxx, dx, dyy, dy, dzz, dz, rxx, rx, ryy, ry, rzz, rz; };
+__device__ __forceinline__ LapDiv make_lapdiv(double dxx, double dx, double dyy, double dy, double dzz, double dz, bool has_y) {
+    LapDiv d;
+    d.dxx = dxx; d.dx = dx; d.dyy = dyy; d.dy = dy; d.dzz = dzz; d.dz = dz;
+    d.rxx = 1.0 / dxx; d.rx = 1.0 / dx; d.rzz = 1.0 / dzz; d.rz = 1.0 / dz;
+    d.ryy = has_y ? 1.0 / dyy : 0.0; d.ry = has_y ? 1.0 / dy : 0.0;
+    return d;
+}
+__device__ __forceinline__ double lap3_inv(double pC, double pE, double pW, double pN, double pS, double pT, double pB,
+                                           double x2, double x1, double y2, double y1, double z2, double z1, const LapDiv &d) {
+    double t = div_inv(x2 * (pE - 2.0 * pC + pW), d.dxx, d.rxx);
+    t = t + div_inv(x1 * (pE - pW), d.dx, d.rx);
+    t = t + div_inv(y2 * (pN - 2.0 * pC + pS), d.dyy, d.ryy);
+    t = t + div_inv(y1 * (pN - pS), d.dy, d.ry);
+    t = t + div_inv(z2 * (pT - 2.0 * pC + pB), d.dzz, d.rzz);
+    t = t + div_inv(z1 * (pT - pB), d.dz, d.rz);
+    return t;
+}
+__device__ __forceinline__ double lap2_inv(double pC, double pE, double pW, double pT, double pB,
+                                           double x2, double x1, double z2, double z1, const LapDiv &d) {
+    double t = div_inv(x2 * (pE - 2.0 * pC + pW), d.dxx, d.rxx);
+    t = t + div_inv(x1 * (pE - pW), d.dx, d.rx);
+    t = t + div_inv(z2 * (pT - 2.0 * pC + pB), d.dzz, d.rzz);
+    t = t + div_inv(z1 * (pT - pB), d.dz, d.rz);
     return t;
 }
 
@@ -100,7 +181,7 @@ __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<do
 /* Thread = one aligned z pair (k0, k0+1) of row j; marches i over [i0, i1).                          */
 /* Algorithmic traffic: 24 B per core point (read p, read rhs, write out).                            */
 /* ------------------------------------------------------------------------------------------------ */
-template <int DIM, int MODE /* 0 Jacobi, 1 residual */>
+template <int DIM, int MODE /* 0 Jacobi, 1 residual */, bool XU /* xix2 constant on this level: the Jacobi diagonal is march-invariant */>
 __global__ void __launch_bounds__(256)
 k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, double *__restrict__ O, const LevelView L,
                 const int ichunk) {
@@ -133,8 +214,17 @@ k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, doub
         cz2a = L.hx2 * z2a; cz2b = L.hx2 * z2b; cz1a = L.hx2 * z1a; cz1b = L.hx2 * z1b;
         two_h = 2.0 * L.hzhx; kx = L.hz2;
     }
-    /* MODE 1 */
-    const double dxx = hx * hx, dx = 2.0 * hx, dyy = hy * hy, dy = 2.0 * hy, dzz = hz * hz, dz = 2.0 * hz;
+    /* MODE 1: the six divisors hx*hx, 2.0*hx, ... are march-invariant */
+    LapDiv dv;
+    if (MODE == 1) dv = make_lapdiv(hx * hx, 2.0 * hx, hy * hy, 2.0 * hy, hz * hz, 2.0 * hz, DIM == 3);
+    /* MODE 0 with XU: den = 4.0*((cx2+cy2)+cz2) is march-invariant too */
+    double den_a = 1.0, den_b = 1.0, rden_a = 1.0, rden_b = 1.0;
+    if (MODE == 0 && XU) {
+        const double cx2 = kx * L.xix2[i0];
+        if (DIM == 3) { const double s = cx2 + cy2; den_a = 4.0 * (s + cz2a); den_b = 4.0 * (s + cz2b); }
+        else { den_a = 4.0 * (cx2 + cz2a); den_b = 4.0 * (cx2 + cz2b); }
+        rden_a = 1.0 / den_a; rden_b = 1.0 / den_b;
+    }
 
     double2 pW = ld2(p + (long long)i0 * plane);          /* plane i0-1 */
     double2 pC = ld2(p + (long long)(i0 + 1) * plane);    /* plane i0   */
@@ -150,7 +240,15 @@ k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, doub
         double2 out;
         if (MODE == 0) {
             const double cx2 = kx * x2, cx1 = kx * x1;
-            if (DIM == 3) {
+            if (XU) {
+                if (DIM == 3) {
+                    out.x = div_inv(relax3_num(pE.x, pW.x, pN.x, pS.x, pC.y, pBa, rr.x, cx2, cx1, hx, cy2, cy1, hy, cz2a, cz1a, hz, two_h), den_a, rden_a);
+                    out.y = div_inv(relax3_num(pE.y, pW.y, pN.y, pS.y, pTb, pC.x, rr.y, cx2, cx1, hx, cy2, cy1, hy, cz2b, cz1b, hz, two_h), den_b, rden_b);
+                } else {
+                    out.x = div_inv(relax2_num(pE.x, pW.x, pC.y, pBa, rr.x, cx2, cx1, hx, cz2a, cz1a, hz, two_h), den_a, rden_a);
+                    out.y = div_inv(relax2_num(pE.y, pW.y, pTb, pC.x, rr.y, cx2, cx1, hx, cz2b, cz1b, hz, two_h), den_b, rden_b);
+                }
+            } else if (DIM == 3) {
                 const double s = cx2 + cy2;
                 out.x = relax3(pE.x, pW.x, pN.x, pS.x, pC.y, pBa, rr.x, cx2, cx1, hx, cy2, cy1, hy, cz2a, cz1a, hz, two_h, 4.0 * (s + cz2a));
                 out.y = relax3(pE.y, pW.y, pN.y, pS.y, pTb, pC.x, rr.y, cx2, cx1, hx, cy2, cy1, hy, cz2b, cz1b, hz, two_h, 4.0 * (s + cz2b));
@@ -160,11 +258,11 @@ k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, doub
             }
         } else {
             if (DIM == 3) {
-                out.x = rr.x - lap3(pC.x, pE.x, pW.x, pN.x, pS.x, pC.y, pBa, x2, x1, y2, y1, z2a, z1a, dxx, dx, dyy, dy, dzz, dz);
-                out.y = rr.y - lap3(pC.y, pE.y, pW.y, pN.y, pS.y, pTb, pC.x, x2, x1, y2, y1, z2b, z1b, dxx, dx, dyy, dy, dzz, dz);
+                out.x = rr.x - lap3_inv(pC.x, pE.x, pW.x, pN.x, pS.x, pC.y, pBa, x2, x1, y2, y1, z2a, z1a, dv);
+                out.y = rr.y - lap3_inv(pC.y, pE.y, pW.y, pN.y, pS.y, pTb, pC.x, x2, x1, y2, y1, z2b, z1b, dv);
             } else {
-                out.x = rr.x - lap2(pC.x, pE.x, pW.x, pC.y, pBa, x2, x1, z2a, z1a, dxx, dx, dzz, dz);
-                out.y = rr.y - lap2(pC.y, pE.y, pW.y, pTb, pC.x, x2, x1, z2b, z1b, dxx, dx, dzz, dz);
+                out.x = rr.x - lap2_inv(pC.x, pE.x, pW.x, pC.y, pBa, x2, x1, z2a, z1a, dv);
+                out.y = rr.y - lap2_inv(pC.y, pE.y, pW.y, pTb, pC.x, x2, x1, z2b, z1b, dv);
             }
         }
         if (has2) st2(o + b, out); else o[b] = out.x;
@@ -227,6 +325,7 @@ k_error_march(const double *__restrict__ P, const double *__restrict__ R, const 
         const double dxx = (DIM == 3) ? hx_c * hx_c : L.hx2, dx = 2.0 * hx_c;
         const double dyy = hy_c * hy_c, dy = 2.0 * hy_c;
         const double dzz = (DIM == 3) ? hz_c * hz_c : L.hz2, dz = 2.0 * hz_c;
+        const LapDiv dv = make_lapdiv(dxx, dx, dyy, dy, dzz, dz, DIM == 3);
         double2 pW = ld2(p + (long long)i0 * plane);
         double2 pC = ld2(p + (long long)(i0 + 1) * plane);
         for (int i = i0; i < i1; ++i) {
@@ -240,11 +339,11 @@ k_error_march(const double *__restrict__ P, const double *__restrict__ R, const 
             const double x2 = L.xix2[i], x1 = L.xixx[i];
             double ta, tb;
             if (DIM == 3) {
-                ta = fabs(lap3(pC.x, pE.x, pW.x, pN.x, pS.x, pC.y, pBa, x2, x1, y2, y1, z2a, z1a, dxx, dx, dyy, dy, dzz, dz) - rr.x);
-                tb = fabs(lap3(pC.y, pE.y, pW.y, pN.y, pS.y, pTb, pC.x, x2, x1, y2, y1, z2b, z1b, dxx, dx, dyy, dy, dzz, dz) - rr.y);
+                ta = fabs(lap3_inv(pC.x, pE.x, pW.x, pN.x, pS.x, pC.y, pBa, x2, x1, y2, y1, z2a, z1a, dv) - rr.x);
+                tb = fabs(lap3_inv(pC.y, pE.y, pW.y, pN.y, pS.y, pTb, pC.x, x2, x1, y2, y1, z2b, z1b, dv) - rr.y);
             } else {
-                ta = fabs(lap2(pC.x, pE.x, pW.x, pC.y, pBa, x2, x1, z2a, z1a, dxx, dx, dzz, dz) - rr.x);
-                tb = fabs(lap2(pC.y, pE.y, pW.y, pTb, pC.x, x2, x1, z2b, z1b, dxx, dx, dzz, dz) - rr.y);
+                ta = fabs(lap2_inv(pC.x, pE.x, pW.x, pC.y, pBa, x2, x1, z2a, z1a, dv) - rr.x);
+                tb = fabs(lap2_inv(pC.y, pE.y, pW.y, pTb, pC.x, x2, x1, z2b, z1b, dv) - rr.y);
             }
             if (norm_order == 1) {
                 num = fmax(num, ta);

@@ -57,6 +57,7 @@ static int set_err(const char *fmt, ...) {
 
 struct Level {
     LevelView v;
+    bool x_uniform;         /* xix2 has one value over the core: the smoother's diagonal does not change along an x-march */
     double *buf[3];         /* SARASMG_PRESSURE, SARASMG_RESIDUAL, SARASMG_TMP */
     double *met[6];         /* device metric arrays (padded, base -1) */
     size_t elems;           /* allocated doubles per array */
@@ -99,6 +100,9 @@ struct sarasmg_solver_s {
     int last_coarse_iters;
     int mean_override;          /* test hook: use mean_value instead of the device-computed RHS mean */
     double mean_value;
+    int prof_max_level;         /* events only for operators on levels <= this */
+    cudaEvent_t user_ev[8];
+    std::vector<std::pair<const void *, size_t>> pinned;   /* caller ranges this handle page-locked */
 };
 
 typedef sarasmg_solver_s S;
@@ -129,6 +133,7 @@ struct ProfScope {
     ProfEntry e;
     ProfScope(S *s_, int kind, int level) : s(s_) {
         on = (s->d.flags & (SARASMG_FLAG_PROFILE | SARASMG_FLAG_TIME_RUN)) != 0;
+        if (on && !(s->d.flags & SARASMG_FLAG_TIME_RUN) && level > s->prof_max_level) on = false;
         if (!on) return;
         e.kind = kind; e.level = level; e.bucket = s->bucket;
         for (cudaEvent_t *ev : {&e.a, &e.b}) {
@@ -361,8 +366,14 @@ static int op_smooth(S *s, int count) {
                 TRY(gs_sweep(s, l));
             } else {
                 const MarchGeom g = march_geom(s, L.v);
-                if (s->planar) k_stencil_march<2, 0><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
-                else k_stencil_march<3, 0><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
+                double *P = L.buf[SARASMG_PRESSURE], *R = L.buf[SARASMG_RESIDUAL], *T = L.buf[SARASMG_TMP];
+                if (s->planar) {
+                    if (L.x_uniform) k_stencil_march<2, 0, true><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
+                    else k_stencil_march<2, 0, false><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
+                } else {
+                    if (L.x_uniform) k_stencil_march<3, 0, true><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
+                    else k_stencil_march<3, 0, false><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
+                }
                 TRY(kcheck(s, "k_stencil_march<jacobi>"));
                 std::swap(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_TMP]);      /* d3:168 */
             }
@@ -383,8 +394,8 @@ static int op_compute_residual(S *s) {
     {
         ProfScope ps(s, SARASMG_K_RESIDUAL, l);
         const MarchGeom g = march_geom(s, L.v);
-        if (s->planar) k_stencil_march<2, 1><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
-        else k_stencil_march<3, 1><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
+        if (s->planar) k_stencil_march<2, 1, false><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
+        else k_stencil_march<3, 1, false><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
         TRY(kcheck(s, "k_stencil_march<residual>"));
     }
     TRY(update_pads(s, l, L.buf[SARASMG_TMP]));
@@ -732,6 +743,8 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     s->t_comp = s->t_tran = 0.0; s->bucket = 0;
     s->last_solve_ms = 0.0; s->last_coarse_iters = 0;
     s->mean_override = 0; s->mean_value = 0.0;
+    s->prof_max_level = 1 << 20;
+    for (int q = 0; q < 8; q++) s->user_ev[q] = nullptr;
     memset(s->prof_ms, 0, sizeof(s->prof_ms));
     memset(s->prof_n, 0, sizeof(s->prof_n));
     for (int q = 0; q < 3; q++) s->d_wall[q] = nullptr;
@@ -775,6 +788,12 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
             CU(cudaMemsetAsync(L.met[m], 0, (size_t)(Fd[dd] + 2) * sizeof(double), s->st));
             if (src[m] && !(s->planar && dd == 1))
                 CU(cudaMemcpyAsync(L.met[m], src[m] + moff[dd], (size_t)Fd[dd] * sizeof(double), cudaMemcpyHostToDevice, s->st));
+        }
+        L.x_uniform = false;
+        if (desc->xix2) {
+            const double *a = desc->xix2 + moff[0] + 1;     /* core entries 0..nx-1 */
+            L.x_uniform = true;
+            for (int i = 1; i < v.nx; i++) if (a[i] != a[0]) { L.x_uniform = false; break; }
         }
         for (int dd = 0; dd < 3; dd++) moff[dd] += (size_t)Fd[dd];
         v.xixx = L.met[0] + 1; v.xix2 = L.met[1] + 1; v.etyy = L.met[2] + 1; v.ety2 = L.met[3] + 1; v.ztzz = L.met[4] + 1; v.ztz2 = L.met[5] + 1;
@@ -846,6 +865,8 @@ int sarasmg_destroy(sarasmg_handle s) {
     for (auto &e : s->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto &e : s->ev_pool) cudaEventDestroy(e);
     cudaEventDestroy(s->ev_solve0); cudaEventDestroy(s->ev_solve1);
+    for (int q = 0; q < 8; q++) if (s->user_ev[q]) cudaEventDestroy(s->user_ev[q]);
+    for (auto &pr : s->pinned) cudaHostUnregister(const_cast<void *>(pr.first));
     cudaStreamDestroy(s->st);
     if ((s->d.flags & SARASMG_FLAG_TIME_RUN) && s->d.rank == 0) {
         /* poisson::~poisson under -DTIME_RUN (poisson.cc:645-652) */
@@ -891,7 +912,31 @@ int sarasmg_download(sarasmg_handle s, double *p_out) {
     return 0;
 }
 
+/* page-lock a caller range once; failures (already pinned by the caller, unsupported memory) only cost speed */
+static void pin_range(S *s, const void *ptr, size_t bytes) {
+    for (auto &pr : s->pinned) if (pr.first == ptr && pr.second >= bytes) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;
+    cudaGetLastError();
+    if (cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess) s->pinned.push_back({ptr, bytes});
+    else cudaGetLastError();
+}
+
+int sarasmg_host_register(sarasmg_handle s, const void *ptr, unsigned long long bytes) {
+    if (!s || !ptr) return set_err("sarasmg_host_register: null argument");
+    CU(cudaSetDevice(s->d.device));
+    pin_range(s, ptr, (size_t)bytes);
+    return 0;
+}
+
 int sarasmg_solve(sarasmg_handle s, double *p_inout, const double *rhs, int *cycles_done, double *residual_history, int *coarse_iters) {
+    if (!s || !p_inout || !rhs) return set_err("sarasmg_solve: null argument");
+    CU(cudaSetDevice(s->d.device));
+    if (!getenv("SARASMG_NO_PIN")) {
+        const LevelView &v0 = s->lev[0].v;
+        const size_t bytes = (size_t)v0.Fx * v0.Fy * v0.Fz * sizeof(double);
+        if (bytes >= ((size_t)1 << 20)) { pin_range(s, p_inout, bytes); pin_range(s, rhs, bytes); }
+    }
     TRY(sarasmg_upload(s, p_inout, rhs));
     TRY(sarasmg_solve_resident(s, cycles_done, residual_history, coarse_iters));
     TRY(sarasmg_download(s, p_inout));
@@ -1126,6 +1171,27 @@ int sarasmg_profile_query(sarasmg_handle s, int kind, int level, double *total_m
 int sarasmg_last_solve_ms(sarasmg_handle s, double *ms) {
     if (!s || !ms) return set_err("null argument");
     *ms = s->last_solve_ms;
+    return 0;
+}
+int sarasmg_set_profile_max_level(sarasmg_handle s, int max_level) {
+    if (!s) return set_err("null handle");
+    s->prof_max_level = max_level;
+    return 0;
+}
+int sarasmg_event_record(sarasmg_handle s, int slot) {
+    ENTER(s);
+    if (slot < 0 || slot >= 8) return set_err("sarasmg_event_record: slot must be 0..7");
+    if (!s->user_ev[slot]) CU(cudaEventCreate(&s->user_ev[slot]));
+    CU(cudaEventRecord(s->user_ev[slot], s->st));
+    return 0;
+}
+int sarasmg_event_elapsed_ms(sarasmg_handle s, int a, int b, double *ms) {
+    ENTER(s);
+    if (a < 0 || a >= 8 || b < 0 || b >= 8 || !ms || !s->user_ev[a] || !s->user_ev[b]) return set_err("sarasmg_event_elapsed_ms: bad slots");
+    CU(cudaEventSynchronize(s->user_ev[b]));
+    float f = 0.f;
+    CU(cudaEventElapsedTime(&f, s->user_ev[a], s->user_ev[b]));
+    *ms = f;
     return 0;
 }
 int sarasmg_debug_set_rhs_mean(sarasmg_handle s, int enable, double value) {
