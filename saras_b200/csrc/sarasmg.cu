@@ -15,6 +15,7 @@
  */
 #include "../../include/sarasmg.h"
 #include "mg_kernels.cuh"
+#include "gs_skew.cuh"
 
 #include <nccl.h>
 
@@ -58,6 +59,11 @@ static int set_err(const char *fmt, ...) {
 struct Level {
     LevelView v;
     bool x_uniform;         /* xix2 has one value over the core: the smoother's diagonal does not change along an x-march */
+    bool z_uniform;         /* ztz2 has one value over the core: the diagonal does not change along a z column */
+    GsPlan gs;              /* skewed Gauss-Seidel sweep: task table + progress counters (device) */
+    int4 *gs_tasks;
+    int *gs_sync;
+    size_t gs_smem;
     double *buf[3];         /* SARASMG_PRESSURE, SARASMG_RESIDUAL, SARASMG_TMP */
     double *met[6];         /* device metric arrays (padded, base -1) */
     size_t elems;           /* allocated doubles per array */
@@ -101,6 +107,7 @@ struct sarasmg_solver_s {
     int mean_override;          /* test hook: use mean_value instead of the device-computed RHS mean */
     double mean_value;
     int prof_max_level;         /* events only for operators on levels <= this */
+    bool gs_legacy;             /* SARASMG_GS_LEGACY: one launch per hyperplane instead of the skewed single-launch sweep */
     cudaEvent_t user_ev[8];
     std::vector<std::pair<const void *, size_t>> pinned;   /* caller ranges this handle page-locked */
 };
@@ -325,11 +332,65 @@ static MarchGeom march_geom(const S *s, const LevelView &v) {
 /* ------------------------------------------------------------------------------------------------ */
 /* operators                                                                                         */
 /* ------------------------------------------------------------------------------------------------ */
+/* builds the task table of the skewed Gauss-Seidel kernel for one level (gs_skew.cuh) */
+static int build_gs_plan(S *s, Level &L) {
+    const LevelView &v = L.v;
+    const int extA = s->planar ? 1 : v.nx, extB = s->planar ? v.nx : v.ny;
+    GsPlan &G = L.gs;
+    int ti = 1;
+    if (!s->planar) {
+        int want = 6;                /* 6 compute warps + halo warp + publisher warp = 256 threads: 128 registers at 2 CTAs per SM */
+        if (const char *e = getenv("SARASMG_GS_TI")) want = std::max(1, std::min(6, atoi(e)));
+        const int nt = (extA + want - 1) / want;
+        ti = (extA + nt - 1) / nt;
+    }
+    G.TI = ti;
+    G.NI = (extA + ti - 1) / ti;
+    G.NJ = (extB + GS_TJ - 1) / GS_TJ;
+    G.NQ = (v.nz + 3) / 4;
+    int zq = 64;
+    if (const char *e = getenv("SARASMG_GS_ZQ")) zq = std::max(1, atoi(e));
+    G.pub = 4;
+    if (const char *e = getenv("SARASMG_GS_PUB")) G.pub = std::max(1, atoi(e));
+    G.ZQ = std::min(zq, G.NQ);
+    G.NZ = std::max(1, G.NQ / G.ZQ);
+    G.ntasks = G.NI * G.NJ * G.NZ;
+    G.z_uniform = L.z_uniform ? 1 : 0;
+    /* ticket order: ideal start time of a task in the systolic schedule; predecessors (I-1,J,Z), (I,J-1,Z), (I,J,Z-1) sort first */
+    struct T { long long key; int I, J, Z; };
+    std::vector<T> ts;
+    ts.reserve(G.ntasks);
+    const long long zspan = (long long)2 * G.ZQ + ti + GS_TJ;
+    for (int Z = 0; Z < G.NZ; Z++)
+        for (int J = 0; J < G.NJ; J++)
+            for (int I = 0; I < G.NI; I++) ts.push_back({(long long)ti * I + (long long)GS_TJ * J + zspan * Z, I, J, Z});
+    std::stable_sort(ts.begin(), ts.end(), [](const T &a, const T &b) { return a.key < b.key; });
+    std::vector<int4> ht(G.ntasks);
+    for (int q = 0; q < G.ntasks; q++) ht[q] = make_int4(ts[q].I, ts[q].J, ts[q].Z, 0);
+    CU(cudaMalloc(&L.gs_tasks, sizeof(int4) * G.ntasks));
+    CU(cudaMemcpyAsync(L.gs_tasks, ht.data(), sizeof(int4) * G.ntasks, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMalloc(&L.gs_sync, sizeof(int) * (G.ntasks + 1)));
+    CU(cudaStreamSynchronize(s->st));
+    G.tasks = L.gs_tasks;
+    G.sync = L.gs_sync;
+    L.gs_smem = sizeof(double) * ((size_t)4 * (ti + 2) * 4 * GS_ROW + (size_t)2 * 2 * G.ZQ * 4);
+    return 0;
+}
+
 static int gs_sweep(S *s, int level) {
     Level &L = s->lev[level];
     const LevelView &v = L.v;
     double *P = L.buf[SARASMG_PRESSURE];
     const double *R = L.buf[SARASMG_RESIDUAL];
+    if (!s->gs_legacy) {
+        /* one launch per sweep: skewed pipeline with ticketed tile tasks (gs_skew.cuh) */
+        const GsPlan &G = L.gs;
+        CU(cudaMemsetAsync(L.gs_sync, 0, sizeof(int) * (G.ntasks + 1), s->st));
+        const dim3 block(32, G.TI + 2, 1);
+        if (s->planar) k_gs_skew<2><<<G.ntasks, block, L.gs_smem, s->st>>>(P, R, v, G);
+        else k_gs_skew<3><<<G.ntasks, block, L.gs_smem, s->st>>>(P, R, v, G);
+        return kcheck(s, "k_gs_skew");
+    }
     if (!s->planar) {
         const int H = v.nx + v.ny + v.nz - 2;
         for (int h = 0; h < H; ++h) {
@@ -744,6 +805,7 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     s->last_solve_ms = 0.0; s->last_coarse_iters = 0;
     s->mean_override = 0; s->mean_value = 0.0;
     s->prof_max_level = 1 << 20;
+    s->gs_legacy = getenv("SARASMG_GS_LEGACY") != nullptr;
     for (int q = 0; q < 8; q++) s->user_ev[q] = nullptr;
     memset(s->prof_ms, 0, sizeof(s->prof_ms));
     memset(s->prof_n, 0, sizeof(s->prof_n));
@@ -795,9 +857,19 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
             L.x_uniform = true;
             for (int i = 1; i < v.nx; i++) if (a[i] != a[0]) { L.x_uniform = false; break; }
         }
+        L.z_uniform = false;
+        if (desc->ztz2) {
+            const double *a = desc->ztz2 + moff[2] + 1;
+            L.z_uniform = true;
+            for (int k = 1; k < v.nz; k++) if (a[k] != a[0]) { L.z_uniform = false; break; }
+        }
+        L.gs_tasks = nullptr; L.gs_sync = nullptr; L.gs_smem = 0;
         for (int dd = 0; dd < 3; dd++) moff[dd] += (size_t)Fd[dd];
         v.xixx = L.met[0] + 1; v.xix2 = L.met[1] + 1; v.etyy = L.met[2] + 1; v.ety2 = L.met[3] + 1; v.ztzz = L.met[4] + 1; v.ztz2 = L.met[5] + 1;
     }
+    for (int l = 0; l <= D; l++) TRY(build_gs_plan(s, s->lev[l]));
+    CU(cudaFuncSetAttribute(k_gs_skew<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_gs_skew<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     {   /* p:360-361 maxCount */
         const LevelView &v = s->lev[D].v;
         s->maxCount = (v.Fx - 1) * (v.Fy - 1) * (v.Fz - 1);
@@ -855,6 +927,7 @@ int sarasmg_destroy(sarasmg_handle s) {
     for (auto &L : s->lev) {
         for (int a = 0; a < 3; a++) cudaFree(L.buf[a]);
         for (int m = 0; m < 6; m++) cudaFree(L.met[m]);
+        cudaFree(L.gs_tasks); cudaFree(L.gs_sync);
     }
     for (int q = 0; q < 3; q++) if (s->d_wall[q]) cudaFree(s->d_wall[q]);
     for (int q = 0; q < 2; q++) { cudaFree(s->xs[q]); cudaFree(s->xr[q]); cudaFree(s->ys[q]); cudaFree(s->yr[q]); }
