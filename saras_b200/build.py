@@ -32,7 +32,8 @@ def build_cuda(force=False, verbose=False):
     srcs = [os.path.join(HERE, "csrc", "sarasmg.cu")]
     deps = srcs + [os.path.join(HERE, "csrc", "mg_kernels.cuh"), os.path.join(ROOT, "include", "sarasmg.h")]
     if force or _stale(out, deps):
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs + ["-lnccl"]
+        extra = os.environ.get("MG_NVCC_EXTRA", "").split()        # tuning experiments: -DMG_MARCH_MINB=5 ...
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs + ["-lnccl"]
         subprocess.run(cmd, check=True)
     return out
 

@@ -36,7 +36,7 @@ struct GsPlan {
     int NQ;                 /* quads per column = ceil(nz / 4) */
     int ntasks;
     int z_uniform;
-    int pub;                /* progress is published every `pub` steps (and at the end) */
+    int tabn;               /* doubles per z table = 4 * (quads of the largest slab) */
     const int4 *tasks;      /* (I, J, Z, -) in ticket order */
     int *sync;              /* [0] ticket counter, [1 + (Z*NJ + J)*NI + I] completed steps of task (I,J,Z) */
 };
@@ -93,12 +93,43 @@ __device__ __forceinline__ int gs_task_steps(const GsPlan &G, const int extA, co
     return nq + ta + tb - 2;
 }
 
-/* exchange slot: kind 0 = NEW quad a thread produced in the previous step, kind 1 = OLD quad two ahead of it */
-#define GS_SLOT(kind, buf, row, e, col) ((((((kind) * 2 + (buf)) * (TI + 2) + (row)) * 4 + (e)) * GS_ROW) + (col))
+/* ---- shared-memory rings (doubles).  A column slot holds one quad (4 doubles, 32 B, contiguous so that cp.async can fill it).
+ *   PO[GS_DP][TI+2][GS_ROW][4]   OLD p quads of the tile's columns and of its plus-side halo columns (row ta+1, col tb+1)
+ *   PN[GS_DP][TI+2][GS_ROW][4]   NEW p quads: written by the compute threads, minus-side halo columns (row 0, col 0) by the halo warp
+ *   RR[GS_DP][TI][32][4]         rhs quads of the tile's columns
+ * quad q of a column lives in ring slot q & (GS_DP-1).                                                                      */
+#define GS_DP 4             /* ring depth = prefetch distance of the tile's own columns, in steps */
+#define GS_DH 3             /* prefetch distance of the halo columns */
+/* a quad is stored as two 16-byte halves, the halves of one row GS_ROW (or 32) columns apart, so that a warp's 128-bit
+ * shared-memory accesses touch consecutive 16-byte words (no bank conflicts) and cp.async can fill each half */
+#define GS_PO(slot, row, col) (po + ((((slot) * (TI + 2) + (row)) * 2 * GS_ROW + (col)) << 1))
+#define GS_PN(slot, row, col) (pn + ((((slot) * (TI + 2) + (row)) * 2 * GS_ROW + (col)) << 1))
+#define GS_RR(slot, row, col) (rr + ((((slot) * TI + (row)) * 2 * 32 + (col)) << 1))
+#define GS_HP (2 * GS_ROW)  /* doubles between the two halves of a PO / PN quad */
+#define GS_HR (2 * 32)      /* ... of an RR quad */
+
+__device__ __forceinline__ void cp_async_quad(double *smem_dst, const int half, const double *gsrc) {   /* 32 B global -> shared, L2 only, asynchronous */
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.cg.shared.global [%2], [%3], 16;"
+                 ::"r"(d), "l"(gsrc), "r"(d + 8u * half), "l"(gsrc + 2) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ quad lds_quad(const double *p, const int half) {
+    quad q;
+    const double2 lo = *reinterpret_cast<const double2 *>(p), hi = *reinterpret_cast<const double2 *>(p + half);
+    q.v[0] = lo.x; q.v[1] = lo.y; q.v[2] = hi.x; q.v[3] = hi.y;
+    return q;
+}
+__device__ __forceinline__ void sts_quad(double *p, const int half, const quad &q) {
+    *reinterpret_cast<double2 *>(p) = make_double2(q.v[0], q.v[1]);
+    *reinterpret_cast<double2 *>(p + half) = make_double2(q.v[2], q.v[3]);
+}
 
 template <int DIM>
 __global__ void __launch_bounds__(256, 2) k_gs_skew(double *P, const double *__restrict__ R, const LevelView L, const GsPlan G) {
-    extern __shared__ double gs_sm[];
+    extern __shared__ __align__(32) double gs_sm[];
     __shared__ int s_task;
     __shared__ int s_done;                              /* steps completed by this CTA (halo warp -> publisher warp) */
     const int TI = G.TI;
@@ -117,25 +148,31 @@ __global__ void __launch_bounds__(256, 2) k_gs_skew(double *P, const double *__r
     const int nsteps = nq + ta + tb - 2;
     const long long strideA = L.plane;                                  /* warp axis (3-D: x) */
     const long long strideB = (DIM == 3) ? (long long)L.pitch : L.plane; /* lane axis (3-D: y, 2-D: x) */
-    /* column (A,B) -> offset of its k = -4 element (so that quad q starts at +4q+4... see QOFF) */
-    const long long colbase = (DIM == 3) ? L.plane + L.pitch : L.plane + L.pitch;   /* index (0,0): one pad plane + one pad row */
+    const long long colbase = L.plane + L.pitch;                        /* column (0,0): one pad plane + one pad row */
 #define GS_COL(A, B) (colbase + (long long)(A) * strideA * (DIM == 3 ? 1 : 0) + (long long)(B) * strideB)
 #define GS_QOFF(q) (4LL * (q) + 1 + MG_LEAD)      /* element offset of k = 4q inside a column */
-    double *sm_tab = gs_sm + 4 * (TI + 2) * 4 * GS_ROW;                 /* z tables of this slab: cz2[4*nq], cz1[4*nq] */
+    double *po = gs_sm;
+    double *pn = po + GS_DP * (TI + 2) * GS_ROW * 4;
+    double *rr = pn + GS_DP * (TI + 2) * GS_ROW * 4;
+    double *sm_tab = rr + GS_DP * TI * 32 * 4;                          /* z tables of this slab: cz2[4*nq], cz1[4*nq] */
     const int ntab = 4 * nq;
     {   /* cz2 = c*ztz2[k], cz1 = c*ztzz[k] with c = hxhy (3-D, d3:145-146) or hx2 (2-D, d2:124-125): the leading products of the z terms */
         const double c = (DIM == 3) ? L.hxhy : L.hx2;
-        for (int q = a * 32 + b; q < ntab; q += nthreads) {
+        for (int q = a * 32 + b; q < ntab; q += (TI + 2) * 32) {
             const int k = 4 * q0 + q;
             const bool ok = k < L.nz;
             sm_tab[q] = ok ? c * L.ztz2[k] : 0.0;
-            sm_tab[2 * G.ZQ * 4 + q] = ok ? c * L.ztzz[k] : 0.0;
+            sm_tab[G.tabn + q] = ok ? c * L.ztzz[k] : 0.0;
         }
     }
     const int idW = (I > 0) ? 1 + (Z * G.NJ + J) * G.NI + (I - 1) : -1;
     const int idL = (J > 0) ? 1 + (Z * G.NJ + (J - 1)) * G.NI + I : -1;
     const int idZ = (Z > 0) ? 1 + ((Z - 1) * G.NJ + J) * G.NI + I : -1;
     int *myprog = G.sync + 1 + (Z * G.NJ + J) * G.NI + I;
+    /* highest slab-local quad that may be loaded from a column: the first quad of the next slab, or (only when nz is a
+     * multiple of 4) the quad holding the k = nz pad */
+    const int nq_ld = (q0 + nq < G.NQ || (L.nz & 3) == 0) ? nq : nq - 1;
+    __syncthreads();                                    /* tables complete */
 
     if (a == TI + 1) {
         /* ------------------------------------------------------------------ publisher warp ------------------------- */
@@ -167,58 +204,27 @@ __global__ void __launch_bounds__(256, 2) k_gs_skew(double *P, const double *__r
         const double *cWm = P + GS_COL(A0 - 1, B0 + b), *cWp = P + GS_COL(A0 + ta, B0 + b);
         const double *cLm = P + GS_COL(A0 + b, B0 - 1), *cLp = P + GS_COL(A0 + b, B0 + tb);
         int seenW = 0, seenL = 0;
-        quad hq[2][4];                                  /* [ring slot][Wm, Wp, Lm, Lp]: loaded in one iteration, stored to the exchange in the next */
-#pragma unroll
-        for (int r = 0; r < 2; r++)
-#pragma unroll
-            for (int w = 0; w < 4; w++)
-#pragma unroll
-                for (int e = 0; e < 4; e++) hq[r][w].v[e] = 0.0;
-        gs_bar(nthreads);                               /* tables written, Z predecessor complete */
-        auto halo_step = [&](const int t, quad(&ld)[4], const quad(&st)[4]) {
-            /* (1) halos of consumer step c2 = t+2: the producers must have completed their step c2 + lag - 1 */
-            const int c2 = t + 2;
+        gs_bar(nthreads);                               /* Z predecessor complete */
+        for (int t = -GS_DP; t < nsteps; ++t) {
+            /* halos of consumer step c = t + GS_DH: the producers must have completed their step c + lag - 1 */
+            const int c = t + GS_DH;
             if (b == 0) {
-                if (idW >= 0) seenW = gs_wait(G.sync + idW, min(c2 + TI, stepsW), seenW);
-                if (idL >= 0) seenL = gs_wait(G.sync + idL, min(c2 + GS_TJ, stepsL), seenL);
+                if (idW >= 0) seenW = gs_wait(G.sync + idW, min(c + TI, stepsW), seenW);
+                if (idL >= 0) seenL = gs_wait(G.sync + idL, min(c + GS_TJ, stepsL), seenL);
             }
             __syncwarp();
             {
-                const int qm = c2 - b, qp = c2 - (ta - 1) - b;
-                if (doW && qm >= 0 && qm < nq) ld[0] = ldq_cg(cWm + GS_QOFF(q0 + qm));
-                if (doW && qp >= 0 && qp < nq) ld[1] = ldq_cg(cWp + GS_QOFF(q0 + qp));
-                const int rm = c2 - b, rp = c2 - b - (tb - 1);
-                if (doL && rm >= 0 && rm < nq) ld[2] = ldq_cg(cLm + GS_QOFF(q0 + rm));
-                if (doL && rp >= 0 && rp < nq) ld[3] = ldq_cg(cLp + GS_QOFF(q0 + rp));
+                const int qm = c - b, qp = c - (ta - 1) - b;        /* quads of consumers (0,b) and (ta-1,b) at step c */
+                if (doW && qm >= 0 && qm < nq) cp_async_quad(GS_PN(qm & (GS_DP - 1), 0, b + 1), GS_HP, cWm + GS_QOFF(q0 + qm));
+                if (doW && qp >= 0 && qp < nq) cp_async_quad(GS_PO(qp & (GS_DP - 1), ta + 1, b + 1), GS_HP, cWp + GS_QOFF(q0 + qp));
+                const int rm = c - b, rp = c - b - (tb - 1);        /* lane b serves row b: consumers (b,0) and (b,tb-1) */
+                if (doL && rm >= 0 && rm < nq) cp_async_quad(GS_PN(rm & (GS_DP - 1), b + 1, 0), GS_HP, cLm + GS_QOFF(q0 + rm));
+                if (doL && rp >= 0 && rp < nq) cp_async_quad(GS_PO(rp & (GS_DP - 1), b + 1, tb + 1), GS_HP, cLp + GS_QOFF(q0 + rp));
             }
-            /* (2) halos of consumer step c1 = t+1 (loaded one iteration ago) into exchange buffer (t+1)&1 */
-            {
-                const int nb = (t + 1) & 1, c1 = t + 1;
-                const int qm = c1 - b, qp = c1 - (ta - 1) - b;
-                if (doW && qm >= 0 && qm < nq) {
-#pragma unroll
-                    for (int e = 0; e < 4; e++) gs_sm[GS_SLOT(0, nb, 0, e, b + 1)] = st[0].v[e];
-                }
-                if (doW && qp >= 0 && qp < nq) {
-#pragma unroll
-                    for (int e = 0; e < 4; e++) gs_sm[GS_SLOT(1, nb, ta + 1, e, b + 1)] = st[1].v[e];
-                }
-                const int rm = c1 - b, rp = c1 - b - (tb - 1);
-                if (doL && rm >= 0 && rm < nq) {
-#pragma unroll
-                    for (int e = 0; e < 4; e++) gs_sm[GS_SLOT(0, nb, b + 1, e, 0)] = st[2].v[e];
-                }
-                if (doL && rp >= 0 && rp < nq) {
-#pragma unroll
-                    for (int e = 0; e < 4; e++) gs_sm[GS_SLOT(1, nb, b + 1, e, tb + 1)] = st[3].v[e];
-                }
-            }
-            gs_bar(nthreads);                           /* end of step t: exchange buffer complete, global stores of step t issued */
+            cp_async_commit();
+            cp_async_wait<GS_DH - 1>();                 /* halos of consumer step t+1 have landed */
+            gs_bar(nthreads);                           /* end of step t: rings complete for step t+1, global stores of step t issued */
             if (b == 0 && t >= 0) { __threadfence_block(); *(volatile int *)&s_done = t + 1; }
-        };
-        for (int t = GS_T0; t < nsteps; t += 2) {       /* unrolled by the ring depth: no register moves behind in-flight loads */
-            halo_step(t, hq[0], hq[1]);
-            if (t + 1 < nsteps) halo_step(t + 1, hq[1], hq[0]);
         }
         return;
     }
@@ -241,99 +247,111 @@ __global__ void __launch_bounds__(256, 2) k_gs_skew(double *P, const double *__r
     }
     const bool zuni = G.z_uniform != 0;
     double den_c = 1.0, rden_c = 1.0;
+    if (zuni && col_ok) { den_c = 4.0 * (s_xy + sm_tab[0]); rden_c = 1.0 / den_c; }
     const long long mycol = GS_COL(Ai, Bi);
     double *pc = P + mycol;
     const double *rc = R + mycol;
-    gs_bar(nthreads);                                   /* tables written, Z predecessor complete */
-    if (zuni && col_ok) { den_c = 4.0 * (s_xy + sm_tab[0]); rden_c = 1.0 / den_c; }
+    gs_bar(nthreads);                                   /* Z predecessor complete */
     double pB = 0.0;
     if (col_ok) pB = ld_cg(pc + GS_QOFF(q0) - 1);       /* new p(i,j,4*q0-1) of the previous slab, or the k = -1 pad */
-    /* highest slab-local quad that may be loaded from the own column: the first quad of the next slab, or (only when nz is a
-     * multiple of 4) the quad holding the k = nz pad */
-    const int nq_ld = (q0 + nq < G.NQ || (L.nz & 3) == 0) ? nq : nq - 1;
-    quad pr[4], rr[2];                                  /* register rings: own OLD quads ql..ql+3 and rhs quads ql, ql+1 */
+    /* shared-memory offsets (doubles) of this thread's column inside one ring slot, and ring strides */
+    const int row_p = 2 * GS_ROW * 2, slot_p = (TI + 2) * row_p, own_p = (a + 1) * row_p + (b + 1) * 2;
+    const int slot_r = TI * 2 * 32 * 2, own_r = a * 2 * 32 * 2 + b * 2;
+    quad cur;                                           /* own OLD quad ql (read from the ring one step earlier as quad ql+1) */
 #pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int e = 0; e < 4; e++) pr[r].v[e] = 0.0;
-#pragma unroll
-    for (int r = 0; r < 2; r++)
-#pragma unroll
-        for (int e = 0; e < 4; e++) rr[r].v[e] = 0.0;
+    for (int e = 0; e < 4; e++) cur.v[e] = 0.0;
 
-    /* one step; oq/on/onn/on3 = ring slots holding own OLD quads ql, ql+1, ql+2, ql+3 (on3 is requested here, onn was
-     * requested one step ago and is published at the end of this step), rq/rqn = rhs quads ql, ql+1 */
-    auto step = [&](const int t, const quad &oq, const quad &on, const quad &onn, quad &on3, const quad &rq, quad &rqn) {
+    for (int t = -GS_DP; t < nsteps; ++t) {
         const int ql = t - a - b;
-        const int buf = t & 1, nb = buf ^ 1;
-        if (col_ok && (ql + 3 >= 0) && (ql + 3 <= nq_ld)) on3 = ldq_cg(pc + GS_QOFF(q0 + ql + 3));
-        if (col_ok && (ql + 1 >= 0) && (ql + 1 < nq)) rqn = ldq_nc(rc + GS_QOFF(q0 + ql + 1));
         const bool active = col_ok && ql >= 0 && ql < nq;
         if (active) {
             const int k0 = 4 * (q0 + ql);
             const int nvalid = min(4, L.nz - k0);
-            double wm[4], wp[4], lm[4], lp[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                lm[e] = gs_sm[GS_SLOT(0, buf, a + 1, e, b)];
-                lp[e] = gs_sm[GS_SLOT(1, buf, a + 1, e, b + 2)];
-                if (DIM == 3) {
-                    wm[e] = gs_sm[GS_SLOT(0, buf, a, e, b + 1)];
-                    wp[e] = gs_sm[GS_SLOT(1, buf, a + 2, e, b + 1)];
-                }
-            }
+            const int sl = ql & (GS_DP - 1), sl1 = (ql + 1) & (GS_DP - 1);
+            const int so = sl * slot_p + own_p, so1 = sl1 * slot_p + own_p;      /* own column in ring slots of quads ql, ql+1 */
+            if (ql == 0) cur = lds_quad(po + so, GS_HP);
+            const quad nxt = lds_quad(po + so1, GS_HP);                  /* own OLD quad ql+1 (.x = pT of the last point) */
+            const quad lm = lds_quad(pn + so - 2, GS_HP);                /* NEW, lane-minus neighbour */
+            const quad lp = lds_quad(po + so + 2, GS_HP);                /* OLD, lane-plus neighbour */
+            const quad rq = lds_quad(rr + sl * slot_r + own_r, GS_HR);
+            const quad tz2 = lds_quad(sm_tab + 4 * ql, 2), tz1 = lds_quad(sm_tab + G.tabn + 4 * ql, 2);
             /* the part of the numerator that does not depend on the k recurrence, in the reference's association */
             double txy[4];
+            if (DIM == 3) {
+                const quad wm = lds_quad(pn + so - row_p, GS_HP);        /* NEW, warp-minus neighbour */
+                const quad wp = lds_quad(po + so + row_p, GS_HP);        /* OLD, warp-plus neighbour */
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                if (DIM == 3) {
-                    double u = cx2 * (wp[e] + wm[e]) * 2.0;
-                    u = u + cx1 * (wp[e] - wm[e]) * hx;
-                    u = u + cy2 * (lp[e] + lm[e]) * 2.0;
-                    u = u + cy1 * (lp[e] - lm[e]) * hy;
+                for (int e = 0; e < 4; e++) {
+                    double u = cx2 * (wp.v[e] + wm.v[e]) * 2.0;
+                    u = u + cx1 * (wp.v[e] - wm.v[e]) * hx;
+                    u = u + cy2 * (lp.v[e] + lm.v[e]) * 2.0;
+                    u = u + cy1 * (lp.v[e] - lm.v[e]) * hy;
                     txy[e] = u;
-                } else {
-                    double u = cx2 * (lp[e] + lm[e]) * 2.0;
-                    u = u + cx1 * (lp[e] - lm[e]) * hx;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    double u = cx2 * (lp.v[e] + lm.v[e]) * 2.0;
+                    u = u + cx1 * (lp.v[e] - lm.v[e]) * hx;
                     txy[e] = u;
                 }
             }
-            quad o;
-            double pb = pB;
+            /* stencil diagonal and its correctly rounded reciprocal (off the recurrence) */
+            double den[4], rden[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                const double pT = (e < 3) ? oq.v[e + 1] : on.v[0];
-                const double cz2 = sm_tab[4 * ql + e], cz1 = sm_tab[2 * G.ZQ * 4 + 4 * ql + e];
-                double u = txy[e] + cz2 * (pT + pb) * 2.0;
-                u = u + cz1 * (pT - pb) * hz;
+                if (zuni) { den[e] = den_c; rden[e] = rden_c; }
+                else { den[e] = 4.0 * (s_xy + tz2.v[e]); rden[e] = 1.0 / den[e]; }
+            }
+            /* the k recurrence: straight-line code; operands outside div_inv's exact range only raise a flag */
+            quad o;
+            double pb = pB;
+            unsigned bad = 0u;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const double pT = (e < 3) ? cur.v[e + 1] : nxt.v[0];
+                double u = txy[e] + tz2.v[e] * (pT + pb) * 2.0;
+                u = u + tz1.v[e] * (pT - pb) * hz;
                 u = u - two_h * rq.v[e];
-                double r;
-                if (zuni) r = div_inv(u, den_c, rden_c);
-                else r = u / (4.0 * (s_xy + cz2));
+                const double r = div_inv_fast(u, den[e], rden[e]);
+                bad |= div_inv_bad(u);
                 if (e < nvalid) pb = r;
                 o.v[e] = r;
+            }
+            if (bad) {                                   /* rare: redo the quad with IEEE divisions */
+                pb = pB;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const double pT = (e < 3) ? cur.v[e + 1] : nxt.v[0];
+                    double u = txy[e] + tz2.v[e] * (pT + pb) * 2.0;
+                    u = u + tz1.v[e] * (pT - pb) * hz;
+                    u = u - two_h * rq.v[e];
+                    const double r = div_ieee(u, den[e]);
+                    if (e < nvalid) pb = r;
+                    o.v[e] = r;
+                }
             }
             pB = pb;
             if (nvalid == 4) stq(pc + GS_QOFF(q0 + ql), o);
             else
                 for (int e = 0; e < nvalid; e++) pc[GS_QOFF(q0 + ql) + e] = o.v[e];
-#pragma unroll
-            for (int e = 0; e < 4; e++) gs_sm[GS_SLOT(0, nb, a + 1, e, b + 1)] = o.v[e];
+            sts_quad(pn + so, GS_HP, o);
+            cur = nxt;
         }
-        if (col_ok && ql + 2 >= 0 && ql + 2 < nq) {     /* OLD quad ql+2 for the minus neighbours' next step */
-#pragma unroll
-            for (int e = 0; e < 4; e++) gs_sm[GS_SLOT(1, nb, a + 1, e, b + 1)] = onn.v[e];
+        /* prefetch GS_DP steps ahead: own OLD quad and rhs quad ql + GS_DP go into the ring slots of quad ql, which nobody
+         * reads any more (this thread just did, its minus neighbours did one step ago) */
+        {
+            const int qn = ql + GS_DP;
+            if (col_ok && qn >= 0 && qn <= nq_ld) cp_async_quad(GS_PO(qn & (GS_DP - 1), a + 1, b + 1), GS_HP, pc + GS_QOFF(q0 + qn));
+            if (col_ok && qn >= 0 && qn < nq) cp_async_quad(GS_RR(qn & (GS_DP - 1), a, b), GS_HR, rc + GS_QOFF(q0 + qn));
+            cp_async_commit();
         }
+        cp_async_wait<GS_DP - 2>();                     /* own quad ql+2 (read by the minus neighbours in the next step) has landed */
         gs_bar(nthreads);
-    };
-    /* unrolled by the ring depth so that no register is moved behind an in-flight load */
-    for (int t = GS_T0; t < nsteps; t += 4) {
-        step(t, pr[0], pr[1], pr[2], pr[3], rr[0], rr[1]);
-        if (t + 1 < nsteps) step(t + 1, pr[1], pr[2], pr[3], pr[0], rr[1], rr[0]);
-        if (t + 2 < nsteps) step(t + 2, pr[2], pr[3], pr[0], pr[1], rr[0], rr[1]);
-        if (t + 3 < nsteps) step(t + 3, pr[3], pr[0], pr[1], pr[2], rr[1], rr[0]);
     }
 #undef GS_COL
 #undef GS_QOFF
 }
-#undef GS_SLOT
+#undef GS_PO
+#undef GS_PN
+#undef GS_RR

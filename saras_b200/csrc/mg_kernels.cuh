@@ -67,6 +67,22 @@ __device__ __forceinline__ double div_inv(const double a, const double b, const 
     return q;
 }
 
+/* the same split in two for straight-line code (gs_skew.cuh): the quotient, and a flag (0/1) that is set when the operand
+ * lies outside the range where the fast sequence is exact; the caller ORs the flags of a group of points and redoes the
+ * group with div_ieee in the (rare) flagged case */
+__device__ __forceinline__ double div_inv_fast(const double a, const double b, const double y) {
+    double q = a * y;
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y, q);
+}
+__device__ __forceinline__ unsigned div_inv_bad(const double a) {
+    const unsigned hi = (unsigned)__double2hiint(a);
+    const unsigned e = (hi >> 20) & 0x7ffu;
+    return (((e - 200u) > 1600u) && (((hi << 1) | (unsigned)__double2loint(a)) != 0u)) ? 1u : 0u;
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* point formulas                                                                                    */
 /* ------------------------------------------------------------------------------------------------ */
@@ -181,8 +197,14 @@ __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<do
 /* Thread = one aligned z pair (k0, k0+1) of row j; marches i over [i0, i1).                          */
 /* Algorithmic traffic: 24 B per core point (read p, read rhs, write out).                            */
 /* ------------------------------------------------------------------------------------------------ */
+#ifndef MG_MARCH_MINB
+#define MG_MARCH_MINB 4      /* resident CTAs per SM the marching kernels are compiled for (register cap 65536 / (256 * MINB)) */
+#endif
+#ifndef MG_ERROR_MINB
+#define MG_ERROR_MINB 2
+#endif
 template <int DIM, int MODE /* 0 Jacobi, 1 residual */, bool XU /* xix2 constant on this level: the Jacobi diagonal is march-invariant */>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MG_MARCH_MINB)
 k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, double *__restrict__ O, const LevelView L,
                 const int ichunk) {
     const int k0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
@@ -301,7 +323,7 @@ __device__ __forceinline__ double block_reduce(double v, double *sm /* >= 32 dou
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MG_ERROR_MINB)
 k_error_march(const double *__restrict__ P, const double *__restrict__ R, const LevelView L, const int ichunk,
               const int norm_order, double hx_c, double hy_c, double hz_c, double *__restrict__ part, const int nblocks) {
     __shared__ double sm[32];

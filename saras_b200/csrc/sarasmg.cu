@@ -348,13 +348,12 @@ static int build_gs_plan(S *s, Level &L) {
     G.NI = (extA + ti - 1) / ti;
     G.NJ = (extB + GS_TJ - 1) / GS_TJ;
     G.NQ = (v.nz + 3) / 4;
-    int zq = 64;
+    int zq = 128;
     if (const char *e = getenv("SARASMG_GS_ZQ")) zq = std::max(1, atoi(e));
-    G.pub = 4;
-    if (const char *e = getenv("SARASMG_GS_PUB")) G.pub = std::max(1, atoi(e));
     G.ZQ = std::min(zq, G.NQ);
     G.NZ = std::max(1, G.NQ / G.ZQ);
     G.ntasks = G.NI * G.NJ * G.NZ;
+    G.tabn = 4 * (G.NQ - (G.NZ - 1) * G.ZQ);
     G.z_uniform = L.z_uniform ? 1 : 0;
     /* ticket order: ideal start time of a task in the systolic schedule; predecessors (I-1,J,Z), (I,J-1,Z), (I,J,Z-1) sort first */
     struct T { long long key; int I, J, Z; };
@@ -373,7 +372,7 @@ static int build_gs_plan(S *s, Level &L) {
     CU(cudaStreamSynchronize(s->st));
     G.tasks = L.gs_tasks;
     G.sync = L.gs_sync;
-    L.gs_smem = sizeof(double) * ((size_t)4 * (ti + 2) * 4 * GS_ROW + (size_t)2 * 2 * G.ZQ * 4);
+    L.gs_smem = sizeof(double) * ((size_t)2 * GS_DP * (ti + 2) * GS_ROW * 4 + (size_t)GS_DP * ti * 32 * 4 + (size_t)2 * G.tabn);
     return 0;
 }
 
@@ -868,8 +867,8 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
         v.xixx = L.met[0] + 1; v.xix2 = L.met[1] + 1; v.etyy = L.met[2] + 1; v.ety2 = L.met[3] + 1; v.ztzz = L.met[4] + 1; v.ztz2 = L.met[5] + 1;
     }
     for (int l = 0; l <= D; l++) TRY(build_gs_plan(s, s->lev[l]));
-    CU(cudaFuncSetAttribute(k_gs_skew<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU(cudaFuncSetAttribute(k_gs_skew<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(k_gs_skew<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_gs_skew<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {   /* p:360-361 maxCount */
         const LevelView &v = s->lev[D].v;
         s->maxCount = (v.Fx - 1) * (v.Fy - 1) * (v.Fz - 1);

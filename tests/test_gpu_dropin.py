@@ -73,6 +73,6 @@ def test_mgtest_driver_prints_reference_lines(tmp_path):
     p = [np.zeros(F)]
     ref = o.mg_solve(p, [np.ones(F)])
     assert len(vals) == ref["cycles"]
-    np.testing.assert_allclose(vals, ref["residuals"], rtol=1e-14, atol=0)       # printed with setprecision(16)
+    np.testing.assert_allclose(vals, ref["residuals"], rtol=1e-12, atol=0)       # printed with setprecision(16); the norm is a parallel reduction
     dev = [float(l.split(": ")[1]) for l in r.stdout.splitlines() if l.startswith("Maximum absolute deviation")]
     assert len(dev) == 1 and abs(dev[0] - ref["max_dev"]) <= 1e-5 * ref["max_dev"]
