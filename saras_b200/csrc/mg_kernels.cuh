@@ -159,22 +159,29 @@ __device__ __forceinline__ LapDiv make_lapdiv(double dxx, double dx, double dyy,
     d.ryy = has_y ? 1.0 / dyy : 0.0; d.ry = has_y ? 1.0 / dy : 0.0;
     return d;
 }
+/* P2: every divisor is an exact power of two (always the case for SARAS grids: the computational coordinate runs over
+ * [0,1] in 2^n intervals, grid.cc:155-164, so hx = 2^l * 2^-n).  Then a / b == a * (1/b) bit for bit -- the exact
+ * quotient and the exact product are the same real number, rounded once -- and the six divisions cost six multiplies. */
+template <bool P2>
+__device__ __forceinline__ double div_by(const double a, const double b, const double y) { return P2 ? a * y : div_inv(a, b, y); }
+template <bool P2>
 __device__ __forceinline__ double lap3_inv(double pC, double pE, double pW, double pN, double pS, double pT, double pB,
                                            double x2, double x1, double y2, double y1, double z2, double z1, const LapDiv &d) {
-    double t = div_inv(x2 * (pE - 2.0 * pC + pW), d.dxx, d.rxx);
-    t = t + div_inv(x1 * (pE - pW), d.dx, d.rx);
-    t = t + div_inv(y2 * (pN - 2.0 * pC + pS), d.dyy, d.ryy);
-    t = t + div_inv(y1 * (pN - pS), d.dy, d.ry);
-    t = t + div_inv(z2 * (pT - 2.0 * pC + pB), d.dzz, d.rzz);
-    t = t + div_inv(z1 * (pT - pB), d.dz, d.rz);
+    double t = div_by<P2>(x2 * (pE - 2.0 * pC + pW), d.dxx, d.rxx);
+    t = t + div_by<P2>(x1 * (pE - pW), d.dx, d.rx);
+    t = t + div_by<P2>(y2 * (pN - 2.0 * pC + pS), d.dyy, d.ryy);
+    t = t + div_by<P2>(y1 * (pN - pS), d.dy, d.ry);
+    t = t + div_by<P2>(z2 * (pT - 2.0 * pC + pB), d.dzz, d.rzz);
+    t = t + div_by<P2>(z1 * (pT - pB), d.dz, d.rz);
     return t;
 }
+template <bool P2>
 __device__ __forceinline__ double lap2_inv(double pC, double pE, double pW, double pT, double pB,
                                            double x2, double x1, double z2, double z1, const LapDiv &d) {
-    double t = div_inv(x2 * (pE - 2.0 * pC + pW), d.dxx, d.rxx);
-    t = t + div_inv(x1 * (pE - pW), d.dx, d.rx);
-    t = t + div_inv(z2 * (pT - 2.0 * pC + pB), d.dzz, d.rzz);
-    t = t + div_inv(z1 * (pT - pB), d.dz, d.rz);
+    double t = div_by<P2>(x2 * (pE - 2.0 * pC + pW), d.dxx, d.rxx);
+    t = t + div_by<P2>(x1 * (pE - pW), d.dx, d.rx);
+    t = t + div_by<P2>(z2 * (pT - 2.0 * pC + pB), d.dzz, d.rzz);
+    t = t + div_by<P2>(z1 * (pT - pB), d.dz, d.rz);
     return t;
 }
 
@@ -203,7 +210,8 @@ __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<do
 #ifndef MG_ERROR_MINB
 #define MG_ERROR_MINB 2
 #endif
-template <int DIM, int MODE /* 0 Jacobi, 1 residual */, bool XU /* xix2 constant on this level: the Jacobi diagonal is march-invariant */>
+template <int DIM, int MODE /* 0 Jacobi, 1 residual */, bool XU /* MODE 0: xix2 constant on this level, the Jacobi diagonal is march-invariant;
+                                                                 MODE 1: the six divisors are powers of two (div_by) */>
 __global__ void __launch_bounds__(256, MG_MARCH_MINB)
 k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, double *__restrict__ O, const LevelView L,
                 const int ichunk) {
@@ -280,11 +288,11 @@ k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, doub
             }
         } else {
             if (DIM == 3) {
-                out.x = rr.x - lap3_inv(pC.x, pE.x, pW.x, pN.x, pS.x, pC.y, pBa, x2, x1, y2, y1, z2a, z1a, dv);
-                out.y = rr.y - lap3_inv(pC.y, pE.y, pW.y, pN.y, pS.y, pTb, pC.x, x2, x1, y2, y1, z2b, z1b, dv);
+                out.x = rr.x - lap3_inv<XU>(pC.x, pE.x, pW.x, pN.x, pS.x, pC.y, pBa, x2, x1, y2, y1, z2a, z1a, dv);
+                out.y = rr.y - lap3_inv<XU>(pC.y, pE.y, pW.y, pN.y, pS.y, pTb, pC.x, x2, x1, y2, y1, z2b, z1b, dv);
             } else {
-                out.x = rr.x - lap2_inv(pC.x, pE.x, pW.x, pC.y, pBa, x2, x1, z2a, z1a, dv);
-                out.y = rr.y - lap2_inv(pC.y, pE.y, pW.y, pTb, pC.x, x2, x1, z2b, z1b, dv);
+                out.x = rr.x - lap2_inv<XU>(pC.x, pE.x, pW.x, pC.y, pBa, x2, x1, z2a, z1a, dv);
+                out.y = rr.y - lap2_inv<XU>(pC.y, pE.y, pW.y, pTb, pC.x, x2, x1, z2b, z1b, dv);
             }
         }
         if (has2) st2(o + b, out); else o[b] = out.x;
@@ -322,7 +330,7 @@ __device__ __forceinline__ double block_reduce(double v, double *sm /* >= 32 dou
     return v;
 }
 
-template <int DIM>
+template <int DIM, bool P2>
 __global__ void __launch_bounds__(256, MG_ERROR_MINB)
 k_error_march(const double *__restrict__ P, const double *__restrict__ R, const LevelView L, const int ichunk,
               const int norm_order, double hx_c, double hy_c, double hz_c, double *__restrict__ part, const int nblocks) {
@@ -361,11 +369,11 @@ k_error_march(const double *__restrict__ P, const double *__restrict__ R, const 
             const double x2 = L.xix2[i], x1 = L.xixx[i];
             double ta, tb;
             if (DIM == 3) {
-                ta = fabs(lap3_inv(pC.x, pE.x, pW.x, pN.x, pS.x, pC.y, pBa, x2, x1, y2, y1, z2a, z1a, dv) - rr.x);
-                tb = fabs(lap3_inv(pC.y, pE.y, pW.y, pN.y, pS.y, pTb, pC.x, x2, x1, y2, y1, z2b, z1b, dv) - rr.y);
+                ta = fabs(lap3_inv<P2>(pC.x, pE.x, pW.x, pN.x, pS.x, pC.y, pBa, x2, x1, y2, y1, z2a, z1a, dv) - rr.x);
+                tb = fabs(lap3_inv<P2>(pC.y, pE.y, pW.y, pN.y, pS.y, pTb, pC.x, x2, x1, y2, y1, z2b, z1b, dv) - rr.y);
             } else {
-                ta = fabs(lap2_inv(pC.x, pE.x, pW.x, pC.y, pBa, x2, x1, z2a, z1a, dv) - rr.x);
-                tb = fabs(lap2_inv(pC.y, pE.y, pW.y, pTb, pC.x, x2, x1, z2b, z1b, dv) - rr.y);
+                ta = fabs(lap2_inv<P2>(pC.x, pE.x, pW.x, pC.y, pBa, x2, x1, z2a, z1a, dv) - rr.x);
+                tb = fabs(lap2_inv<P2>(pC.y, pE.y, pW.y, pTb, pC.x, x2, x1, z2b, z1b, dv) - rr.y);
             }
             if (norm_order == 1) {
                 num = fmax(num, ta);
@@ -646,6 +654,72 @@ __global__ void __launch_bounds__(256) k_prolong_add(const double *__restrict__ 
 #undef PC
     const long long idx = mg_at(Lf, i, j, k);
     Pf[idx] = v + Pf[idx];
+}
+
+/* The same operator as an x-marching kernel (used for every level with >= 2 coarse points along z per warp lane).
+ * A thread owns the coarse cell (j2, k2) and walks i2: the four coarse values of plane i2 it needs stay in registers
+ * and become the "minus" plane of the next step, every fine row is touched with one aligned 128-bit load and one
+ * 128-bit store per thread (fine k = 2*k2 sits on a 16-byte boundary), and a warp covers 512 contiguous bytes of each
+ * of the four fine rows (2i2 | 2i2+1, 2j2 | 2j2+1).  Sums are left-associated in the order of d3:310-365 / d2:248-270. */
+template <int DIM>
+__global__ void __launch_bounds__(256) k_prolong_march(const double *__restrict__ C, const LevelView Lc, double *__restrict__ Pf,
+                                                       const LevelView Lf, const int ichunk) {
+    const int k2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j2 = (DIM == 3) ? (blockIdx.y * blockDim.y + threadIdx.y) : 0;
+    if (k2 >= Lc.nz || j2 >= Lc.ny) return;
+    const int i0 = blockIdx.z * ichunk;                 /* coarse planes [i0, i1) */
+    const int i1 = min(i0 + ichunk, Lc.nx);
+    const bool hk = (k2 + 1 < Lc.nz);                   /* fine k = 2*k2+1 exists */
+    const bool hj = (DIM == 3) && (j2 + 1 < Lc.ny);     /* fine j = 2*j2+1 exists */
+    const double *c = C + (long long)(j2 + 1) * Lc.pitch + (k2 + 1 + MG_LEAD);
+    double *f = Pf + (long long)((DIM == 3 ? 2 * j2 : 0) + 1) * Lf.pitch + (2 * k2 + 1 + MG_LEAD);
+    const int cp = Lc.pitch, fp = Lf.pitch;
+    /* coarse values: [di][dj][dk] relative to (i2, j2, k2); entries beyond the array edge are never used */
+    double a00, a01 = 0.0, a10 = 0.0, a11 = 0.0;        /* plane i2 */
+    {
+        const double *q = c + (long long)(i0 + 1) * Lc.plane;
+        a00 = q[0];
+        if (hk) a01 = q[1];
+        if (hj) { a10 = q[cp]; if (hk) a11 = q[cp + 1]; }
+    }
+    for (int i2 = i0; i2 < i1; ++i2) {
+        const bool hi = (i2 + 1 < Lc.nx);               /* fine i = 2*i2+1 exists */
+        double b00 = 0.0, b01 = 0.0, b10 = 0.0, b11 = 0.0;   /* plane i2+1 */
+        if (hi) {
+            const double *q = c + (long long)(i2 + 2) * Lc.plane;
+            b00 = q[0];
+            if (hk) b01 = q[1];
+            if (hj) { b10 = q[cp]; if (hk) b11 = q[cp + 1]; }
+        }
+        double *fe = f + (long long)(2 * i2 + 1) * Lf.plane;         /* fine plane 2*i2 */
+        double *fo = fe + Lf.plane;                                   /* fine plane 2*i2+1 */
+        /* even i */
+        {
+            double2 v;
+            v.x = a00;
+            v.y = (a00 + a01) / 2.0;
+            if (hk) { double2 o = ld2(fe); o.x = v.x + o.x; o.y = v.y + o.y; st2(fe, o); } else fe[0] = v.x + fe[0];
+            if (hj) {
+                v.x = (a00 + a10) / 2.0;
+                v.y = (a00 + a01 + a10 + a11) / 4.0;
+                double *g = fe + fp;
+                if (hk) { double2 o = ld2(g); o.x = v.x + o.x; o.y = v.y + o.y; st2(g, o); } else g[0] = v.x + g[0];
+            }
+        }
+        if (hi) {
+            double2 v;
+            v.x = (a00 + b00) / 2.0;
+            v.y = (a00 + a01 + b00 + b01) / 4.0;
+            if (hk) { double2 o = ld2(fo); o.x = v.x + o.x; o.y = v.y + o.y; st2(fo, o); } else fo[0] = v.x + fo[0];
+            if (hj) {
+                v.x = (a00 + a10 + b00 + b10) / 4.0;
+                v.y = (a00 + b00 + a10 + a01 + b10 + b01 + a11 + b11) / 8.0;
+                double *g = fo + fp;
+                if (hk) { double2 o = ld2(g); o.x = v.x + o.x; o.y = v.y + o.y; st2(g, o); } else g[0] = v.x + g[0];
+            }
+        }
+        a00 = b00; a01 = b01; a10 = b10; a11 = b11;
+    }
 }
 
 /* ------------------------------------------------------------------------------------------------ */

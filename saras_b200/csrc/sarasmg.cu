@@ -107,6 +107,8 @@ struct sarasmg_solver_s {
     int mean_override;          /* test hook: use mean_value instead of the device-computed RHS mean */
     double mean_value;
     int prof_max_level;         /* events only for operators on levels <= this */
+    bool prolong_legacy;        /* SARASMG_PROLONG_LEGACY: thread-per-fine-point prolongation kernel */
+    bool no_pow2;               /* SARASMG_NO_POW2: keep the general exact-division path even when the divisors are powers of two (tests) */
     bool gs_legacy;             /* SARASMG_GS_LEGACY: one launch per hyperplane instead of the skewed single-launch sweep */
     cudaEvent_t user_ev[8];
     std::vector<std::pair<const void *, size_t>> pinned;   /* caller ranges this handle page-locked */
@@ -162,6 +164,17 @@ static inline int kcheck(S *s, const char *what) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return set_err("kernel launch %s failed: %s", what, cudaGetErrorString(e));
     return 0;
+}
+
+/* x is an exact power of two whose reciprocal is a normal double: dividing by x equals multiplying by 1/x bit for bit */
+static inline bool is_pow2(double x) {
+    int e = 0;
+    if (!(x > 0.0) || !std::isfinite(x)) return false;
+    return std::frexp(x, &e) == 0.5 && e > -1000 && e < 1000;
+}
+/* the six divisors of the Laplacian bracket (d3:100-105): hx*hx, 2hx, hy*hy, 2hy, hz*hz, 2hz (2-D: dxx, dzz passed in) */
+static inline bool divisors_pow2(bool planar, double dxx, double hx, double hy, double dzz, double hz) {
+    return is_pow2(dxx) && is_pow2(2.0 * hx) && is_pow2(dzz) && is_pow2(2.0 * hz) && (planar || (is_pow2(hy * hy) && is_pow2(2.0 * hy)));
 }
 
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
@@ -454,8 +467,15 @@ static int op_compute_residual(S *s) {
     {
         ProfScope ps(s, SARASMG_K_RESIDUAL, l);
         const MarchGeom g = march_geom(s, L.v);
-        if (s->planar) k_stencil_march<2, 1, false><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
-        else k_stencil_march<3, 1, false><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.buf[SARASMG_TMP], L.v, g.ichunk);
+        double *P = L.buf[SARASMG_PRESSURE], *R = L.buf[SARASMG_RESIDUAL], *T = L.buf[SARASMG_TMP];
+        const bool p2 = divisors_pow2(s->planar, L.v.hx * L.v.hx, L.v.hx, L.v.hy, L.v.hz * L.v.hz, L.v.hz) && !s->no_pow2;
+        if (s->planar) {
+            if (p2) k_stencil_march<2, 1, true><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
+            else k_stencil_march<2, 1, false><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
+        } else {
+            if (p2) k_stencil_march<3, 1, true><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
+            else k_stencil_march<3, 1, false><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
+        }
         TRY(kcheck(s, "k_stencil_march<residual>"));
     }
     TRY(update_pads(s, l, L.buf[SARASMG_TMP]));
@@ -488,14 +508,28 @@ static int op_prolong(S *s) {
     Level &Lc = s->lev[pLevel];
     Level &Lf = s->lev[s->vLevel];
     ProfScope ps(s, SARASMG_K_PROLONG, s->vLevel);
-    if (s->planar) {
-        k_prolong_add<2><<<dim3(cdiv(Lf.v.nz, 128), 1, Lf.v.nx), dim3(128, 1, 1), 0, s->st>>>(Lc.buf[SARASMG_PRESSURE], Lc.v, Lf.buf[SARASMG_PRESSURE], Lf.v);
-    } else {
-        int bx = 64, by = 4;
-        while (bx > 4 && bx / 2 >= Lf.v.nz) { bx /= 2; by *= 2; }
-        k_prolong_add<3><<<dim3(cdiv(Lf.v.nz, bx), cdiv(Lf.v.ny, by), Lf.v.nx), dim3(bx, by, 1), 0, s->st>>>(Lc.buf[SARASMG_PRESSURE], Lc.v, Lf.buf[SARASMG_PRESSURE], Lf.v);
+    if (s->prolong_legacy) {
+        if (s->planar) {
+            k_prolong_add<2><<<dim3(cdiv(Lf.v.nz, 128), 1, Lf.v.nx), dim3(128, 1, 1), 0, s->st>>>(Lc.buf[SARASMG_PRESSURE], Lc.v, Lf.buf[SARASMG_PRESSURE], Lf.v);
+        } else {
+            int bx = 64, by = 4;
+            while (bx > 4 && bx / 2 >= Lf.v.nz) { bx /= 2; by *= 2; }
+            k_prolong_add<3><<<dim3(cdiv(Lf.v.nz, bx), cdiv(Lf.v.ny, by), Lf.v.nx), dim3(bx, by, 1), 0, s->st>>>(Lc.buf[SARASMG_PRESSURE], Lc.v, Lf.buf[SARASMG_PRESSURE], Lf.v);
+        }
+        return kcheck(s, "k_prolong_add");
     }
-    return kcheck(s, "k_prolong_add");
+    {   /* marching kernel: threads over the coarse (k2, j2) cells, x in chunks sized for >= ~8 CTAs per SM */
+        int bx = 32, by = 8;
+        if (s->planar) { bx = 128; by = 1; }
+        else while (bx > 4 && bx / 2 >= Lc.v.nz) { bx /= 2; by *= 2; }
+        const unsigned gx = cdiv(Lc.v.nz, bx), gy = s->planar ? 1 : cdiv(Lc.v.ny, by);
+        int ichunk = 32;
+        while (ichunk > 2 && (long long)gx * gy * cdiv(Lc.v.nx, ichunk) < 148LL * 8) ichunk /= 2;
+        const dim3 grid(gx, gy, cdiv(Lc.v.nx, ichunk)), block(bx, by, 1);
+        if (s->planar) k_prolong_march<2><<<grid, block, 0, s->st>>>(Lc.buf[SARASMG_PRESSURE], Lc.v, Lf.buf[SARASMG_PRESSURE], Lf.v, ichunk);
+        else k_prolong_march<3><<<grid, block, 0, s->st>>>(Lc.buf[SARASMG_PRESSURE], Lc.v, Lf.buf[SARASMG_PRESSURE], Lf.v, ichunk);
+    }
+    return kcheck(s, "k_prolong_march");
 }
 
 static int ensure_part(S *s, size_t n) {
@@ -534,8 +568,16 @@ static int op_compute_error(S *s, int norm, double *value) {
     {
         ProfScope ps(s, SARASMG_K_ERROR, 0);
         const Level &Lv = s->lev[s->vLevel];        /* d3:411 uses hx(vLevel) */
-        if (s->planar) k_error_march<2><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, g.ichunk, norm, L.v.hx, L.v.hy, L.v.hz, s->d_part, nb);
-        else k_error_march<3><<<g.grid, g.block, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, g.ichunk, norm, Lv.v.hx, Lv.v.hy, Lv.v.hz, s->d_part, nb);
+        double *P = L.buf[SARASMG_PRESSURE], *R = L.buf[SARASMG_RESIDUAL];
+        if (s->planar) {
+            const bool p2 = divisors_pow2(true, L.v.hx2, L.v.hx, 0.0, L.v.hz2, L.v.hz) && !s->no_pow2;
+            if (p2) k_error_march<2, true><<<g.grid, g.block, 0, s->st>>>(P, R, L.v, g.ichunk, norm, L.v.hx, L.v.hy, L.v.hz, s->d_part, nb);
+            else k_error_march<2, false><<<g.grid, g.block, 0, s->st>>>(P, R, L.v, g.ichunk, norm, L.v.hx, L.v.hy, L.v.hz, s->d_part, nb);
+        } else {
+            const bool p2 = divisors_pow2(false, Lv.v.hx * Lv.v.hx, Lv.v.hx, Lv.v.hy, Lv.v.hz * Lv.v.hz, Lv.v.hz) && !s->no_pow2;
+            if (p2) k_error_march<3, true><<<g.grid, g.block, 0, s->st>>>(P, R, L.v, g.ichunk, norm, Lv.v.hx, Lv.v.hy, Lv.v.hz, s->d_part, nb);
+            else k_error_march<3, false><<<g.grid, g.block, 0, s->st>>>(P, R, L.v, g.ichunk, norm, Lv.v.hx, Lv.v.hy, Lv.v.hz, s->d_part, nb);
+        }
         TRY(kcheck(s, "k_error_march"));
         k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part, nb, 2, (norm == 1) ? 1u : 0u, s->d_scal);
         TRY(kcheck(s, "k_reduce_final"));
@@ -805,6 +847,8 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     s->mean_override = 0; s->mean_value = 0.0;
     s->prof_max_level = 1 << 20;
     s->gs_legacy = getenv("SARASMG_GS_LEGACY") != nullptr;
+    s->no_pow2 = getenv("SARASMG_NO_POW2") != nullptr;
+    s->prolong_legacy = getenv("SARASMG_PROLONG_LEGACY") != nullptr;
     for (int q = 0; q < 8; q++) s->user_ev[q] = nullptr;
     memset(s->prof_ms, 0, sizeof(s->prof_ms));
     memset(s->prof_n, 0, sizeof(s->prof_n));

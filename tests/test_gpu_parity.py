@@ -63,8 +63,19 @@ def test_smooth_bitexact(case, gs):
     s.close()
 
 
+def _select_path(monkeypatch, path):
+    """'fast': power-of-two divisors multiply by the exact reciprocal, marching prolongation (what production runs, because
+    SARAS grids always have 2^n intervals).  'general': the exact-division sequence and the thread-per-point prolongation,
+    kept for grids whose spacing is not a power of two; both must be bit-identical to the oracle."""
+    if path == "general":
+        monkeypatch.setenv("SARASMG_NO_POW2", "1")
+        monkeypatch.setenv("SARASMG_PROLONG_LEGACY", "1")
+
+
 @pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
-def test_residual_coarsen_prolong_bitexact(case):
+@pytest.mark.parametrize("path", ["fast", "general"])
+def test_residual_coarsen_prolong_bitexact(case, path, monkeypatch):
+    _select_path(monkeypatch, path)
     o, s = _mk(case)
     for level in range(o.depth):
         _, F = o.level_dims(level)
@@ -125,7 +136,9 @@ def test_solve_coarsest_bitexact(case):
 
 @pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
 @pytest.mark.parametrize("norm", [1, 2])
-def test_compute_error(case, norm):
+@pytest.mark.parametrize("path", ["fast", "general"])
+def test_compute_error(case, norm, path, monkeypatch):
+    _select_path(monkeypatch, path)
     o, s = _mk(case)
     _, F = o.level_dims(0)
     _load_both(o, s, 0, mo.PRESSURE, seeded_field(F, 100))
