@@ -208,8 +208,14 @@ __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<do
 #define MG_MARCH_MINB 4      /* resident CTAs per SM the marching kernels are compiled for (register cap 65536 / (256 * MINB)) */
 #endif
 #ifndef MG_ERROR_MINB
-#define MG_ERROR_MINB 2
+#define MG_ERROR_MINB 4
 #endif
+/* software prefetch distance of the marching kernels, in x planes (0 = off): each thread asks L2 for the lines it will
+ * load MG_PF_DIST iterations later, so the demand loads see L2 latency instead of HBM latency without holding registers */
+#ifndef MG_PF_DIST
+#define MG_PF_DIST 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int DIM, int MODE /* 0 Jacobi, 1 residual */, bool XU /* MODE 0: xix2 constant on this level, the Jacobi diagonal is march-invariant;
                                                                  MODE 1: the six divisors are powers of two (div_by) */>
 __global__ void __launch_bounds__(256, MG_MARCH_MINB)
@@ -260,6 +266,10 @@ k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, doub
     double2 pC = ld2(p + (long long)(i0 + 1) * plane);    /* plane i0   */
     for (int i = i0; i < i1; ++i) {
         const long long b = (long long)(i + 1) * plane;
+        if (MG_PF_DIST > 0 && i + MG_PF_DIST < i1) {
+            prefetch_l2(p + b + (long long)(MG_PF_DIST + 1) * plane);
+            prefetch_l2(r + b + (long long)MG_PF_DIST * plane);
+        }
         const double2 pE = ld2(p + b + plane);
         const double2 rr = ld2(r + b);
         const double pBa = p[b - 1];        /* (i, j, k0-1) */
@@ -360,6 +370,10 @@ k_error_march(const double *__restrict__ P, const double *__restrict__ R, const 
         double2 pC = ld2(p + (long long)(i0 + 1) * plane);
         for (int i = i0; i < i1; ++i) {
             const long long b = (long long)(i + 1) * plane;
+            if (MG_PF_DIST > 0 && i + MG_PF_DIST < i1) {
+                prefetch_l2(p + b + (long long)(MG_PF_DIST + 1) * plane);
+                prefetch_l2(r + b + (long long)MG_PF_DIST * plane);
+            }
             const double2 pE = ld2(p + b + plane);
             const double2 rr = ld2(r + b);
             const double pBa = p[b - 1];
@@ -854,6 +868,121 @@ __global__ void __launch_bounds__(1024) k_coarse_solve(double *P, const double *
     }
     cta_impose_bc<DIM>(P, L, B);
     if (tid == 0) *iters_out = iter;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Coarsest-level solve, several ranks: agglomerated.  The reference iterates {imposeBC (halo exchange   */
+/* + wall BCs); per-rank lexicographic GS sweep; global MAX of the residual} until the MAX drops under    */
+/* mgTolerance (d3:190-247) -- hundreds of latency-bound exchange + all-reduce rounds on a grid of a few  */
+/* points per rank.  Here every rank all-gathers the (tiny) coarsest arrays of all ranks once, and ONE    */
+/* CTA replays the whole loop on the nb rank-blocks exactly as the nb reference ranks would: each block   */
+/* keeps its own pads, exchanges faces with its neighbour blocks (x phase, then y phase carrying the      */
+/* fresh x pads), applies its own wall BCs, and is swept by its own block-GS; the convergence test uses   */
+/* the MAX over all blocks.  Every rank computes the same bits and keeps its own block, so no scatter     */
+/* and no per-iteration collective is needed.                                                            */
+/* ------------------------------------------------------------------------------------------------ */
+struct CoarseBlock {
+    int nbr[4];                     /* face neighbours (block ids) left, right, front, back; -1 = none */
+    int wall[4];                    /* 1 where that face is a physical non-periodic wall of the domain */
+    const double *xixx, *xix2, *etyy, *ety2;    /* this block's x / y metric arrays of the coarsest level (index base -1 applied) */
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(1024) k_coarse_solve_blocks(double *P, const double *R, const long long stride, const int nblk,
+                                                             const CoarseBlock *__restrict__ tab, const LevelView L,
+                                                             const int wall_mode, const int z_lo_mode, const int z_hi_mode,
+                                                             const double tol, const int maxCount, int *iters_out) {
+    __shared__ double sm[32];
+    __shared__ double s_max;
+    __shared__ CoarseBlock s_tab[16];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int q = tid; q < nblk; q += nthr) s_tab[q] = tab[q];
+    __syncthreads();
+    const bool planar = (DIM == 2);
+    const int H = L.nx + L.ny + L.nz - 2;
+    const int nij = L.nx * L.ny;
+    const long long cnt = (long long)nij * L.nz;
+    const int jlo = planar ? 0 : -1, nj = planar ? 1 : L.Fy;
+    const int xE = L.nx - 1, yE = L.ny - 1;
+    int iter = 0;
+    while (true) {
+        /* ---- imposeBC of every block: updatePads x phase, y phase, then walls x, y, z (d3:575-668) ---- */
+        {
+            const long long per = (long long)nj * L.Fz;
+            for (long long q = tid; q < per * nblk; q += nthr) {
+                const int b = (int)(q / per);
+                const long long w = q % per;
+                const int j = jlo + (int)(w / L.Fz), k = (int)(w % L.Fz) - 1;
+                double *A = P + b * stride;
+                const int nl = s_tab[b].nbr[0], nr = s_tab[b].nbr[1];
+                if (nl >= 0) A[mg_at(L, -1, j, k)] = P[nl * stride + mg_at(L, xE - 1, j, k)];
+                if (nr >= 0) A[mg_at(L, xE + 1, j, k)] = P[nr * stride + mg_at(L, 1, j, k)];
+            }
+            __syncthreads();
+        }
+        if (DIM == 3) {
+            const long long per = (long long)L.Fx * L.Fz;
+            for (long long q = tid; q < per * nblk; q += nthr) {
+                const int b = (int)(q / per);
+                const long long w = q % per;
+                const int i = (int)(w / L.Fz) - 1, k = (int)(w % L.Fz) - 1;
+                double *A = P + b * stride;
+                const int nf = s_tab[b].nbr[2], nk = s_tab[b].nbr[3];
+                if (nf >= 0) A[mg_at(L, i, -1, k)] = P[nf * stride + mg_at(L, i, yE - 1, k)];
+                if (nk >= 0) A[mg_at(L, i, yE + 1, k)] = P[nk * stride + mg_at(L, i, 1, k)];
+            }
+            __syncthreads();
+        }
+        for (int b = 0; b < nblk; ++b) {
+            const int lo = s_tab[b].wall[0] ? wall_mode : FACE_NONE, hi = s_tab[b].wall[1] ? wall_mode : FACE_NONE;
+            if (lo | hi) face_op<0>(P + b * stride, L, lo, hi, nullptr, planar, tid, nthr);
+        }
+        __syncthreads();
+        if (DIM == 3) {
+            for (int b = 0; b < nblk; ++b) {
+                const int lo = s_tab[b].wall[2] ? wall_mode : FACE_NONE, hi = s_tab[b].wall[3] ? wall_mode : FACE_NONE;
+                if (lo | hi) face_op<1>(P + b * stride, L, lo, hi, nullptr, planar, tid, nthr);
+            }
+            __syncthreads();
+        }
+        for (int b = 0; b < nblk; ++b) face_op<2>(P + b * stride, L, z_lo_mode, z_hi_mode, nullptr, planar, tid, nthr);
+        __syncthreads();
+        if (iter < 0) break;                            /* trailing imposeBC done */
+
+        /* ---- block Gauss-Seidel: hyperplane wavefront inside every block, all blocks at once ---- */
+        for (int h = 0; h < H; ++h) {
+            for (int q = tid; q < nij * nblk; q += nthr) {
+                const int b = q / nij, w = q % nij;
+                const int i = w / L.ny, j = w % L.ny;
+                const int k = h - i - j;
+                if (k >= 0 && k < L.nz) {
+                    LevelView Lb = L;
+                    Lb.xixx = s_tab[b].xixx; Lb.xix2 = s_tab[b].xix2; Lb.etyy = s_tab[b].etyy; Lb.ety2 = s_tab[b].ety2;
+                    gs_point<DIM>(P + b * stride, R + b * stride, Lb, i, j, k);
+                }
+            }
+            __syncthreads();
+        }
+        double m = -1.0e-10;
+        for (long long q = tid; q < cnt * nblk; q += nthr) {
+            const int b = (int)(q / cnt);
+            const long long w = q % cnt;
+            const int k = (int)(w % L.nz);
+            const int j = (int)((w / L.nz) % L.ny);
+            const int i = (int)(w / ((long long)L.nz * L.ny));
+            LevelView Lb = L;
+            Lb.xixx = s_tab[b].xixx; Lb.xix2 = s_tab[b].xix2; Lb.etyy = s_tab[b].etyy; Lb.ety2 = s_tab[b].ety2;
+            m = fmax(m, resid_abs_point<DIM>(P + b * stride, R + b * stride, Lb, i, j, k));
+        }
+        m = block_reduce<true>(m, sm);
+        if (tid == 0) s_max = m;
+        __syncthreads();
+        const double gmax = s_max;
+        __syncthreads();
+        bool stop = gmax < tol;
+        if (!stop) { iter += 1; stop = iter > maxCount; }
+        if (stop) { if (tid == 0) *iters_out = iter; iter = -1; }      /* one more pass through imposeBC, then out */
+    }
 }
 
 /* misc */

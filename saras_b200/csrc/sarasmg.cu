@@ -93,6 +93,12 @@ struct sarasmg_solver_s {
     bool has_comm;
     double *xs[2], *xr[2], *ys[2], *yr[2];
     double *d_gather;           /* n_proc * 4 doubles */
+    /* agglomerated coarsest-level solve (k_coarse_solve_blocks): all ranks' coarsest arrays, block table, metric copies */
+    double *agg_P, *agg_R;      /* n_proc * lev[D].elems doubles each */
+    CoarseBlock *agg_tab;
+    double *agg_met;            /* n_proc * 2 * ((Fx+2) + (Fy+2)) doubles: xixx, xix2, etyy, ety2 of every rank, coarsest level */
+    bool agg_ok;
+    bool coarse_legacy;         /* SARASMG_COARSE_LEGACY: host-driven loop, one halo exchange + all-gather per iteration */
     /* instrumentation */
     long long launches;
     std::vector<ProfEntry> pending;
@@ -621,6 +627,56 @@ static void bc_plan(const S *s, BcPlan &B) {
     B.planar = s->planar;
 }
 
+/* One-time exchange for the agglomerated coarsest solve: every rank learns every rank's face neighbours, wall flags and
+ * coarsest-level x / y metric arrays (the z arrays are common: z is never split, parallel.cc:89-92). */
+static int setup_agglomeration(S *s) {
+    const sarasmg_desc &d = s->d;
+    const int np = d.n_proc;
+    if (np > 16 || s->D == 0) return 0;                 /* table size of the kernel; D == 0 would need every rank's wall planes */
+    Level &L = s->lev[s->D];
+    const LevelView &v = L.v;
+    const int mx = v.Fx + 2, my = v.Fy + 2;
+    const int rec = 8 + 2 * mx + 2 * my;                /* doubles per rank: 4 neighbours, 4 wall flags, xixx, xix2, etyy, ety2 */
+    std::vector<double> mine(rec, 0.0), all((size_t)rec * np, 0.0);
+    int m[6];
+    bc_modes(s, m);                                     /* which x / y faces are physical walls does not depend on zeroBC */
+    for (int f = 0; f < 4; f++) { mine[f] = d.face_ranks[f]; mine[4 + f] = (m[f] != FACE_NONE) ? 1.0 : 0.0; }
+    CU(cudaMemcpyAsync(mine.data() + 8, L.met[0], mx * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(mine.data() + 8 + mx, L.met[1], mx * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(mine.data() + 8 + 2 * mx, L.met[2], my * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(mine.data() + 8 + 2 * mx + my, L.met[3], my * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    double *d_mine = nullptr, *d_all = nullptr;
+    CU(cudaMalloc(&d_mine, rec * sizeof(double)));
+    CU(cudaMalloc(&d_all, (size_t)rec * np * sizeof(double)));
+    CU(cudaMemcpyAsync(d_mine, mine.data(), rec * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    NC(ncclAllGather(d_mine, d_all, (size_t)rec, ncclDouble, s->comm, s->st));
+    CU(cudaMemcpyAsync(all.data(), d_all, (size_t)rec * np * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaFree(d_mine)); CU(cudaFree(d_all));
+
+    const int met_rec = 2 * mx + 2 * my;
+    std::vector<double> met((size_t)met_rec * np);
+    std::vector<CoarseBlock> tab(np);
+    CU(cudaMalloc(&s->agg_met, met.size() * sizeof(double)));
+    for (int r = 0; r < np; r++) {
+        const double *a = all.data() + (size_t)r * rec;
+        for (int f = 0; f < 4; f++) { tab[r].nbr[f] = (int)a[f]; tab[r].wall[f] = (int)a[4 + f]; }
+        if (s->planar) { tab[r].nbr[2] = tab[r].nbr[3] = -1; tab[r].wall[2] = tab[r].wall[3] = 0; }
+        memcpy(met.data() + (size_t)r * met_rec, a + 8, met_rec * sizeof(double));
+        double *base = s->agg_met + (size_t)r * met_rec;
+        tab[r].xixx = base + 1; tab[r].xix2 = base + mx + 1; tab[r].etyy = base + 2 * mx + 1; tab[r].ety2 = base + 2 * mx + my + 1;
+    }
+    CU(cudaMemcpyAsync(s->agg_met, met.data(), met.size() * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMalloc(&s->agg_tab, np * sizeof(CoarseBlock)));
+    CU(cudaMemcpyAsync(s->agg_tab, tab.data(), np * sizeof(CoarseBlock), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMalloc(&s->agg_P, (size_t)np * L.elems * sizeof(double)));
+    CU(cudaMalloc(&s->agg_R, (size_t)np * L.elems * sizeof(double)));
+    CU(cudaStreamSynchronize(s->st));
+    s->agg_ok = true;
+    return 0;
+}
+
 /* solve (d3:190-247, d2:150-199) */
 static int op_solve_coarsest(S *s, int *iters, bool sync) {
     const int l = s->vLevel;
@@ -646,7 +702,29 @@ static int op_solve_coarsest(S *s, int *iters, bool sync) {
         }
         return 0;
     }
-    /* several ranks: host-driven loop, one halo exchange and one MAX all-reduce per iteration (d3:195,233) */
+    if (s->agg_ok && !s->coarse_legacy && l == s->D) {
+        /* several ranks, agglomerated: all-gather the coarsest arrays once, replay all rank-blocks in one CTA on every rank */
+        int m[6];
+        bc_modes(s, m);
+        const int wall = d.test_poisson ? (s->zeroBC ? FACE_NEG_MIRROR : FACE_WALL) : FACE_MIRROR;
+        if (wall == FACE_WALL) return set_err("solve: non-homogeneous Dirichlet BC on level %d", l);
+        NC(ncclGroupStart());
+        NC(ncclAllGather(L.buf[SARASMG_PRESSURE], s->agg_P, L.elems, ncclDouble, s->comm, s->st));
+        NC(ncclAllGather(L.buf[SARASMG_RESIDUAL], s->agg_R, L.elems, ncclDouble, s->comm, s->st));
+        NC(ncclGroupEnd());
+        if (s->planar) k_coarse_solve_blocks<2><<<1, 1024, 0, s->st>>>(s->agg_P, s->agg_R, (long long)L.elems, d.n_proc, s->agg_tab, L.v, wall, m[4], m[5], d.mg_tolerance, s->maxCount, s->d_iters);
+        else k_coarse_solve_blocks<3><<<1, 1024, 0, s->st>>>(s->agg_P, s->agg_R, (long long)L.elems, d.n_proc, s->agg_tab, L.v, wall, m[4], m[5], d.mg_tolerance, s->maxCount, s->d_iters);
+        TRY(kcheck(s, "k_coarse_solve_blocks"));
+        CU(cudaMemcpyAsync(L.buf[SARASMG_PRESSURE], s->agg_P + (size_t)d.rank * L.elems, L.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+        CU(cudaMemcpyAsync(s->h_iters, s->d_iters, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+        if (sync) {
+            CU(cudaStreamSynchronize(s->st));
+            if (iters) *iters = *s->h_iters;
+            s->last_coarse_iters = *s->h_iters;
+        }
+        return 0;
+    }
+    /* several ranks, legacy: host-driven loop, one halo exchange and one MAX all-reduce per iteration (d3:195,233) */
     int iterCount = 0;
     const long long cnt = (long long)L.v.nx * L.v.ny * L.v.nz;
     const unsigned nb = std::min(cdiv(cnt, 256), 1024u);
@@ -755,7 +833,7 @@ static int solve_core(S *s, const double *in_p, const double *in_rhs, int *cycle
         TRY(op_compute_error(s, d.res_type, &mgResidual));
         if (d.res_type == 0) CU(cudaStreamSynchronize(s->st));
         s->last_coarse_iters = *s->h_iters;
-        if (s->last_coarse_iters > s->maxCount && d.n_proc == 1 && d.print_residual && d.rank == 0)
+        if (s->last_coarse_iters > s->maxCount && (d.n_proc == 1 || (s->agg_ok && !s->coarse_legacy)) && d.print_residual && d.rank == 0)
             printf("WARNING: Iterations for solution at coarsest level not converging.\n");    /* d3:240-243 */
         if (hist) hist[i] = mgResidual;
         if (citers) citers[i] = s->last_coarse_iters;
@@ -855,6 +933,8 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     for (int q = 0; q < 3; q++) s->d_wall[q] = nullptr;
     for (int q = 0; q < 2; q++) s->xs[q] = s->xr[q] = s->ys[q] = s->yr[q] = nullptr;
     s->d_gather = nullptr;
+    s->agg_P = s->agg_R = nullptr; s->agg_tab = nullptr; s->agg_met = nullptr; s->agg_ok = false;
+    s->coarse_legacy = getenv("SARASMG_COARSE_LEGACY") != nullptr;
     CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     CU(cudaEventCreate(&s->ev_solve0));
     CU(cudaEventCreate(&s->ev_solve1));
@@ -952,6 +1032,7 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
             CU(cudaMalloc(&s->ys[q], yc * sizeof(double))); CU(cudaMalloc(&s->yr[q], yc * sizeof(double)));
         }
         CU(cudaMalloc(&s->d_gather, (size_t)desc->n_proc * 8 * sizeof(double)));
+        TRY(setup_agglomeration(s));
     }
     s->d.nccl_id = nullptr;     /* the caller's buffers are not retained */
     s->d.hx = s->d.hy = s->d.hz = s->d.hx2 = s->d.hz2 = s->d.hzhx = s->d.hxhy = s->d.hyhz = s->d.hxhyhz = nullptr;
@@ -975,6 +1056,7 @@ int sarasmg_destroy(sarasmg_handle s) {
     for (int q = 0; q < 3; q++) if (s->d_wall[q]) cudaFree(s->d_wall[q]);
     for (int q = 0; q < 2; q++) { cudaFree(s->xs[q]); cudaFree(s->xr[q]); cudaFree(s->ys[q]); cudaFree(s->yr[q]); }
     cudaFree(s->d_gather);
+    cudaFree(s->agg_P); cudaFree(s->agg_R); cudaFree(s->agg_tab); cudaFree(s->agg_met);
     cudaFree(s->d_part); cudaFree(s->d_scal); cudaFree(s->d_iters);
     cudaFreeHost(s->h_scal); cudaFreeHost(s->h_iters);
     cudaFree(s->d_in_p); cudaFree(s->d_in_rhs);

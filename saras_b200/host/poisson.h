@@ -25,6 +25,8 @@
 #include "plainsf.h"
 #include "grid.h"
 
+static_assert(sizeof(real) == sizeof(double), "the B200 multigrid path is fp64 only: build SARAS with -DREAL_DOUBLE");
+
 struct sarasmg_solver_s;
 
 class poisson {

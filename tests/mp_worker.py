@@ -106,8 +106,14 @@ def run_gpu(rank, world, local):
         assert np.array_equal(got, ref), "%s: rank %d level %d array %d differs, max |d| = %g" % (
             what, rank, level, which, float(np.max(np.abs(got - ref))))
 
-    for case in gpu_cases(world):
-        base = {k: v for k, v in case.items() if k != "name"}
+    cases = gpu_cases(world)
+    # the first case once more with the host-driven coarsest solve (one halo exchange + all-gather per iteration)
+    cases.append(dict(cases[0], name=cases[0]["name"] + "_coarse_legacy", _env="SARASMG_COARSE_LEGACY"))
+    for case in cases:
+        base = {k: v for k, v in case.items() if k not in ("name", "_env")}
+        os.environ.pop("SARASMG_COARSE_LEGACY", None)
+        if case.get("_env"):
+            os.environ[case["_env"]] = "1"
         for gs in (0, 1):
             cfg = dict(base, gsSmooth=gs, vcCount=6, resType=2, mgTolerance=1e-7)
             o = Oracle(**cfg)
