@@ -137,6 +137,10 @@ def run_gpu(rank, world, local):
                     same(o, s, level, mo.PRESSURE, what + " smooth(%d)" % count)
             # residual -> restriction (reads edge pads) -> prolongation
             for level in range(D):
+                # fresh arrays per level: the oracle's Jacobi swap exchanges P and TMP of ALL levels at once (d3:168), so
+                # after the smoothing block above its other levels' names point at stale buffers (dead data in a real cycle)
+                load_both(o, s, level, mo.PRESSURE, 30 + level)
+                load_both(o, s, level, mo.RESIDUAL, 50 + level, 3.0)
                 o.set_level(level); s.set_level(level)
                 o.set_zero_bc(1); s.set_zero_bc(1)
                 o.compute_residual(); s.compute_residual()
@@ -145,6 +149,7 @@ def run_gpu(rank, world, local):
                 same(o, s, level + 1, mo.RESIDUAL, what + " coarsen")
             # coarsest solve with its global MAX test
             load_both(o, s, D, mo.PRESSURE, 77, 0.0)
+            load_both(o, s, D, mo.RESIDUAL, 78, 0.01)
             o.set_level(D); s.set_level(D)
             it_ref = o.solve_coarsest(); it_got = s.solve_coarsest()
             assert it_ref == it_got, (what, it_ref, it_got)
