@@ -310,8 +310,14 @@ def run_b200(a):
     dom = next((e for e in per_level if e["level"] == 0 and e["op"] == "smooth"), None)
     roofline = None
     if dom:
-        roofline = dict(bound="hbm", achieved=dom["gbs"], peak=peak, unit="GB/s", frac=dom["gbs"] / peak, traffic=None,
-                        kernel="level-0 smoother sweep (%s)" % ("k_gs_* lexicographic Gauss-Seidel" if a.smoother == "gs" else "k_stencil_march<3,0> Jacobi"),
+        traffic = None      # DRAM bytes per launch of this kernel from the committed ncu capture (same grid, same layout only)
+        if a.gpus == 1 and a.index == 10 and a.mesh == "uniform":
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_1025_n1.json")))[a.smoother]["bytes"]
+            except Exception:
+                traffic = None
+        roofline = dict(bound="hbm", achieved=dom["gbs"], peak=peak, unit="GB/s", frac=dom["gbs"] / peak, traffic=traffic,
+                        kernel="level-0 smoother sweep (%s)" % ("k_gs_skew<3> lexicographic Gauss-Seidel" if a.smoother == "gs" else "k_stencil_tma<0> Jacobi, TMA-staged x-march"),
                         algorithmic_bytes_per_launch=BYTES_PER_LUP["smooth"] * level_points_local[0], avg_launch_ms=dom["avg_ms"],
                         peak_source=peak_src)
 

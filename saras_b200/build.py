@@ -26,13 +26,18 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build_cuda(force=False, verbose=False):
+def build_cuda(force=False, verbose=False, variant=None, defines=()):
+    """variant: build saras_b200/lib/variants/libsarasmg_<variant>.so with extra -D flags (kernel tuning experiments are
+    compiled here, where nvcc costs no GPU time, and selected on the GPU box with SARASMG_LIB=<path>)."""
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libsarasmg.so")
+    if variant:
+        os.makedirs(os.path.join(LIBDIR, "variants"), exist_ok=True)
+        out = os.path.join(LIBDIR, "variants", "libsarasmg_%s.so" % variant)
     srcs = [os.path.join(HERE, "csrc", "sarasmg.cu")]
-    deps = srcs + [os.path.join(HERE, "csrc", "mg_kernels.cuh"), os.path.join(ROOT, "include", "sarasmg.h")]
+    deps = srcs + [os.path.join(HERE, "csrc", f) for f in ("mg_kernels.cuh", "gs_skew.cuh", "mg_tma.cuh")] + [os.path.join(ROOT, "include", "sarasmg.h")]
     if force or _stale(out, deps):
-        extra = os.environ.get("MG_NVCC_EXTRA", "").split()        # tuning experiments: -DMG_MARCH_MINB=5 ...
+        extra = os.environ.get("MG_NVCC_EXTRA", "").split() + list(defines)     # tuning experiments: -DMG_MARCH_MINB=5 ...
         cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs + ["-lnccl"]
         subprocess.run(cmd, check=True)
     return out
@@ -51,4 +56,8 @@ def build_all(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    if "--variant" in sys.argv:
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        print(build_cuda(force=True, verbose="-v" in sys.argv, variant=name, defines=[a for a in sys.argv if a.startswith("-D")]))
+    else:
+        build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)

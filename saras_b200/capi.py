@@ -59,9 +59,10 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError("saras_b200: %s is missing -- run `python -m saras_b200.build` (no CPU fallback exists)" % LIB_PATH)
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    path = os.environ.get("SARASMG_LIB", LIB_PATH)     # tuning: a variant built with `python -m saras_b200.build --variant NAME -D...`
+    if not os.path.exists(path):
+        raise RuntimeError("saras_b200: %s is missing -- run `python -m saras_b200.build` (no CPU fallback exists)" % path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     vp, ip = C.c_void_p, C.POINTER(C.c_int)
     lib.sarasmg_last_error.restype = C.c_char_p
     lib.sarasmg_get_unique_id.argtypes = [C.c_void_p]

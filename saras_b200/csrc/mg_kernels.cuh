@@ -544,6 +544,90 @@ __global__ void __launch_bounds__(256) k_face(double *A, const LevelView L, cons
                  (long long)gridDim.x * blockDim.x);
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* All six face operations of one imposeBC / self-neighbour updatePads / pad zeroing in ONE launch.     */
+/* The reference applies x, then y, then z, each over full planes including the pads of the other        */
+/* directions (d3:578-667), so an edge or corner pad ends up with the value of the LAST operation that    */
+/* writes it, and that operation read a pad the previous one had written.  Here every pad point is        */
+/* written once, by a thread of its last-writing operation, which resolves the chain of sources           */
+/* backwards (z source, then y, then x) down to a point this kernel does not write (a core point, or a   */
+/* pad whose direction has no operation: halo data).  Same values, no ordering between threads needed.   */
+/* ------------------------------------------------------------------------------------------------ */
+struct FaceModes { int m[6]; const double *xwall, *ywall, *zwall; };      /* x lo, x hi, y lo, y hi, z lo, z hi */
+
+__device__ __forceinline__ int face_src(const int mode, const bool lo, const int E) {   /* source index of a pad along one axis */
+    if (mode == FACE_PERIODIC) return lo ? E - 1 : 1;
+    return lo ? 1 : E - 1;                              /* mirror, negative mirror */
+}
+template <int DIM>
+__device__ __forceinline__ double face_resolve(const double *A, const LevelView &L, const FaceModes &F, int i, int j, int k) {
+    const int xE = L.nx - 1, yE = L.ny - 1, zE = L.nz - 1;
+    bool neg = false;
+    {
+        const int side = (k == -1) ? 4 : (k == zE + 1) ? 5 : -1;
+        const int md = side >= 0 ? F.m[side] : FACE_NONE;
+        if (md != FACE_NONE) {
+            if (md == FACE_ZERO) return 0.0;
+            if (md == FACE_WALL) return (DIM == 2) ? F.zwall[i + 1] : F.zwall[(long long)(i + 1) * L.Fy + (j + 1)];
+            k = face_src(md, side == 4, zE);
+            neg ^= (md == FACE_NEG_MIRROR);
+        }
+    }
+    if (DIM == 3) {
+        const int side = (j == -1) ? 2 : (j == yE + 1) ? 3 : -1;
+        const int md = side >= 0 ? F.m[side] : FACE_NONE;
+        if (md != FACE_NONE) {
+            if (md == FACE_ZERO) return 0.0;
+            if (md == FACE_WALL) { const double w = F.ywall[(long long)(i + 1) * L.Fz + (k + 1)]; return neg ? -w : w; }
+            j = face_src(md, side == 2, yE);
+            neg ^= (md == FACE_NEG_MIRROR);
+        }
+    }
+    {
+        const int side = (i == -1) ? 0 : (i == xE + 1) ? 1 : -1;
+        const int md = side >= 0 ? F.m[side] : FACE_NONE;
+        if (md != FACE_NONE) {
+            if (md == FACE_ZERO) return 0.0;
+            if (md == FACE_WALL) { const double w = (DIM == 2) ? F.xwall[k + 1] : F.xwall[(long long)(j + 1) * L.Fz + (k + 1)]; return neg ? -w : w; }
+            i = face_src(md, side == 0, xE);
+            neg ^= (md == FACE_NEG_MIRROR);
+        }
+    }
+    const double v = A[mg_at(L, i, j, k)];
+    return neg ? -v : v;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_faces(double *A, const LevelView L, const FaceModes F) {
+    const int jlo = (DIM == 2) ? 0 : -1, nj = (DIM == 2) ? 1 : L.Fy;
+    const int yE = L.ny - 1, zE = L.nz - 1, xE = L.nx - 1;
+    const long long nZ = (F.m[4] | F.m[5]) ? (long long)L.Fx * nj : 0;                   /* (i, j) columns of the z faces */
+    const long long nY = (DIM == 3 && (F.m[2] | F.m[3])) ? (long long)L.Fx * L.Fz : 0;   /* (i, k) of the y faces */
+    const long long nX = (F.m[0] | F.m[1]) ? (long long)nj * L.Fz : 0;                   /* (j, k) of the x faces */
+    const long long tot = nZ + nY + nX;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+        if (q < nZ) {
+            const int i = (int)(q / nj) - 1, j = jlo + (int)(q % nj);
+            if (F.m[4] != FACE_NONE) A[mg_at(L, i, j, -1)] = face_resolve<DIM>(A, L, F, i, j, -1);
+            if (F.m[5] != FACE_NONE) A[mg_at(L, i, j, zE + 1)] = face_resolve<DIM>(A, L, F, i, j, zE + 1);
+        } else if (q < nZ + nY) {
+            const long long w = q - nZ;
+            const int i = (int)(w / L.Fz) - 1, k = (int)(w % L.Fz) - 1;
+            /* a z operation on this side writes the point after the y operation: its thread owns it */
+            if ((k == -1 && F.m[4] != FACE_NONE) || (k == zE + 1 && F.m[5] != FACE_NONE)) continue;
+            if (F.m[2] != FACE_NONE) A[mg_at(L, i, -1, k)] = face_resolve<DIM>(A, L, F, i, -1, k);
+            if (F.m[3] != FACE_NONE) A[mg_at(L, i, yE + 1, k)] = face_resolve<DIM>(A, L, F, i, yE + 1, k);
+        } else {
+            const long long w = q - nZ - nY;
+            const int j = jlo + (int)(w / L.Fz), k = (int)(w % L.Fz) - 1;
+            if ((k == -1 && F.m[4] != FACE_NONE) || (k == zE + 1 && F.m[5] != FACE_NONE)) continue;
+            if (DIM == 3 && ((j == -1 && F.m[2] != FACE_NONE) || (j == yE + 1 && F.m[3] != FACE_NONE))) continue;
+            if (F.m[0] != FACE_NONE) A[mg_at(L, -1, j, k)] = face_resolve<DIM>(A, L, F, -1, j, k);
+            if (F.m[1] != FACE_NONE) A[mg_at(L, xE + 1, j, k)] = face_resolve<DIM>(A, L, F, xE + 1, j, k);
+        }
+    }
+}
+
 /* y-row pack/unpack for the inter-GPU halo (MPI_Type_vector of d3:492-497): row j of every x plane <-> contiguous buffer */
 __global__ void __launch_bounds__(256) k_pack_y(const double *__restrict__ A, const LevelView L, const int j, double *__restrict__ buf) {
     const long long cnt = (long long)L.Fx * L.Fz;
@@ -574,6 +658,59 @@ __global__ void __launch_bounds__(256) k_unpack_x(double *__restrict__ A, const 
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
         const int j = (planar ? 0 : -1) + (int)(q / L.Fz), k = (int)(q % L.Fz) - 1;
         A[mg_at(L, i, j, k)] = buf[q];
+    }
+}
+
+/* Fused halo staging for the two-phase exchange (x faces first, then y rows that carry the fresh x pads):
+ *   k_pack_x2          planes i = 1 and i = nx-2            -> send buffers of the left / right neighbour
+ *   k_unpack_x_pack_y  receive buffers -> pads i = -1 / nx, and rows j = 1 / ny-2 (their i = -1 / nx entries taken from the
+ *                      receive buffers, so no thread depends on another thread's pad write) -> y send buffers
+ *   k_unpack_y2        receive buffers -> pads j = -1 / ny
+ * Null pointers switch a side off. */
+__global__ void __launch_bounds__(256) k_pack_x2(const double *__restrict__ A, const LevelView L, const int planar,
+                                                 double *__restrict__ lo, double *__restrict__ hi) {
+    const int nj = planar ? 1 : L.Fy;
+    const long long cnt = (long long)nj * L.Fz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
+        const int j = (planar ? 0 : -1) + (int)(q / L.Fz), k = (int)(q % L.Fz) - 1;
+        if (lo) lo[q] = A[mg_at(L, 1, j, k)];
+        if (hi) hi[q] = A[mg_at(L, L.nx - 2, j, k)];
+    }
+}
+__global__ void __launch_bounds__(256) k_unpack_x_pack_y(double *__restrict__ A, const LevelView L, const int planar,
+                                                         const double *__restrict__ xr_lo, const double *__restrict__ xr_hi,
+                                                         double *__restrict__ ys_lo, double *__restrict__ ys_hi) {
+    const int nj = planar ? 1 : L.Fy;
+    const long long cx = (xr_lo || xr_hi) ? (long long)nj * L.Fz : 0;
+    const long long cy = (ys_lo || ys_hi) ? (long long)L.Fx * L.Fz : 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cx + cy; q += (long long)gridDim.x * blockDim.x) {
+        if (q < cx) {
+            const int j = (planar ? 0 : -1) + (int)(q / L.Fz), k = (int)(q % L.Fz) - 1;
+            if (xr_lo) A[mg_at(L, -1, j, k)] = xr_lo[q];
+            if (xr_hi) A[mg_at(L, L.nx, j, k)] = xr_hi[q];
+        } else {
+            const long long w = q - cx;
+            const int i = (int)(w / L.Fz) - 1, k = (int)(w % L.Fz) - 1;
+            for (int side = 0; side < 2; side++) {
+                double *dst = side ? ys_hi : ys_lo;
+                if (!dst) continue;
+                const int j = side ? L.ny - 2 : 1;
+                double v;
+                if (i == -1 && xr_lo) v = xr_lo[(long long)(j + 1) * L.Fz + (k + 1)];
+                else if (i == L.nx && xr_hi) v = xr_hi[(long long)(j + 1) * L.Fz + (k + 1)];
+                else v = A[mg_at(L, i, j, k)];
+                dst[w] = v;
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_unpack_y2(double *__restrict__ A, const LevelView L, const double *__restrict__ yr_lo,
+                                                   const double *__restrict__ yr_hi) {
+    const long long cnt = (long long)L.Fx * L.Fz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q / L.Fz) - 1, k = (int)(q % L.Fz) - 1;
+        if (yr_lo) A[mg_at(L, i, -1, k)] = yr_lo[q];
+        if (yr_hi) A[mg_at(L, i, L.ny, k)] = yr_hi[q];
     }
 }
 
@@ -983,6 +1120,167 @@ __global__ void __launch_bounds__(1024) k_coarse_solve_blocks(double *P, const d
         if (!stop) { iter += 1; stop = iter > maxCount; }
         if (stop) { if (tid == 0) *iters_out = iter; iter = -1; }      /* one more pass through imposeBC, then out */
     }
+}
+
+/* The same loop with the blocks resident in SHARED memory (used whenever they fit; nblk = 1 is the single-rank solve).
+ * Per block: pressure and rhs in compact padded layout, the stencil diagonal and its correctly rounded reciprocal per core
+ * point (the GS update divides by the diagonal: div_inv reproduces the IEEE quotient from the stored reciprocal), and the
+ * coefficient products of every axis.  A GS hyperplane step is then a handful of shared-memory loads and ~30 fp64
+ * operations between two barriers instead of a chain of global loads and a division. */
+template <int DIM>
+__global__ void __launch_bounds__(256) k_coarse_solve_smem(double *Pg, const double *Rg, const long long stride, const int nblk,
+                                                          const CoarseBlock *__restrict__ tab, const LevelView L,
+                                                          const int wall_mode, const int z_lo_mode, const int z_hi_mode, const int p2,
+                                                          const double tol, const int maxCount, int *iters_out) {
+    extern __shared__ double cs_sm[];
+    __shared__ double sm[32];
+    __shared__ double s_max;
+    __shared__ CoarseBlock s_tab[16];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int q = tid; q < nblk; q += nthr) s_tab[q] = tab[q];
+    const int Fx = L.Fx, Fy = (DIM == 2) ? 1 : L.Fy, Fz = L.Fz;      /* 2-D: only the live j = 0 row is kept */
+    const int jo = (DIM == 2) ? 0 : 1;                               /* row offset of j = 0 */
+    const int vol = Fx * Fy * Fz;
+    const int nx = L.nx, ny = L.ny, nz = L.nz, nij = nx * ny, cnt = nij * nz;
+    double *sP = cs_sm, *sR = sP + nblk * vol, *sD = sR + nblk * vol, *sI = sD + nblk * cnt;
+    double *cx2 = sI + nblk * cnt, *cx1 = cx2 + nblk * nx, *cy2 = cx1 + nblk * nx, *cy1 = cy2 + nblk * ny;
+    double *cz2 = cy1 + nblk * ny, *cz1 = cz2 + nz, *mx2 = cz1 + nz, *mx1 = mx2 + nblk * nx, *my2 = mx1 + nblk * nx, *my1 = my2 + nblk * ny;
+    double *mz2 = my1 + nblk * ny, *mz1 = mz2 + nz;
+#define CS_AT(i, j, k) ((((i) + 1) * Fy + ((j) + jo)) * Fz + ((k) + 1))
+    __syncthreads();
+    for (int q = tid; q < nblk * vol; q += nthr) {
+        const int b = q / vol, w = q % vol;
+        const int k = w % Fz - 1, j = (w / Fz) % Fy - jo, i = w / (Fz * Fy) - 1;
+        sP[q] = Pg[b * stride + mg_at(L, i, j, k)];
+        sR[q] = Rg[b * stride + mg_at(L, i, j, k)];
+    }
+    const double kxc = (DIM == 3) ? L.hyhz : L.hz2, kyc = L.hzhx, kzc = (DIM == 3) ? L.hxhy : L.hx2;
+    for (int q = tid; q < nblk * nx; q += nthr) { const int b = q / nx, i = q % nx; mx2[q] = s_tab[b].xix2[i]; mx1[q] = s_tab[b].xixx[i]; cx2[q] = kxc * mx2[q]; cx1[q] = kxc * mx1[q]; }
+    if (DIM == 3)
+        for (int q = tid; q < nblk * ny; q += nthr) { const int b = q / ny, j = q % ny; my2[q] = s_tab[b].ety2[j]; my1[q] = s_tab[b].etyy[j]; cy2[q] = kyc * my2[q]; cy1[q] = kyc * my1[q]; }
+    for (int q = tid; q < nz; q += nthr) { mz2[q] = L.ztz2[q]; mz1[q] = L.ztzz[q]; cz2[q] = kzc * mz2[q]; cz1[q] = kzc * mz1[q]; }
+    __syncthreads();
+    for (int q = tid; q < nblk * cnt; q += nthr) {
+        const int b = q / cnt, w = q % cnt;
+        const int k = w % nz, j = (w / nz) % ny, i = w / (nz * ny);
+        const double d = (DIM == 3) ? 4.0 * (cx2[b * nx + i] + cy2[b * ny + j] + cz2[k]) : 4.0 * (cx2[b * nx + i] + cz2[k]);
+        sD[q] = d;
+        sI[q] = 1.0 / d;
+    }
+    const double hx = L.hx, hy = L.hy, hz = L.hz;
+    const double two_h = (DIM == 3) ? 2.0 * L.hxhyhz : 2.0 * L.hzhx;
+    const LapDiv dv = make_lapdiv(hx * hx, 2.0 * hx, hy * hy, 2.0 * hy, hz * hz, 2.0 * hz, DIM == 3);
+    const int H = nx + ny + nz - 2;
+    const int xE = nx - 1, yE = ny - 1, zE = nz - 1;
+    const int sj = Fz, si = Fy * Fz;
+    __syncthreads();
+    int iter = 0;
+    while (true) {
+        /* ---- imposeBC of every block: x pads, y pads (with the fresh x pads), then walls x, y, z ---- */
+        for (int q = tid; q < nblk * Fy * Fz; q += nthr) {
+            const int b = q / (Fy * Fz), w = q % (Fy * Fz);
+            const int nl = s_tab[b].nbr[0], nr = s_tab[b].nbr[1];
+            if (nl >= 0) sP[b * vol + w] = sP[nl * vol + xE * si + w];                   /* i = -1 <- neighbour's i = xE-1 */
+            if (nr >= 0) sP[b * vol + (xE + 2) * si + w] = sP[nr * vol + 2 * si + w];    /* i = xE+1 <- neighbour's i = 1 */
+        }
+        __syncthreads();
+        if (DIM == 3) {
+            for (int q = tid; q < nblk * Fx * Fz; q += nthr) {
+                const int b = q / (Fx * Fz), w = q % (Fx * Fz);
+                const int o = (w / Fz) * si + (w % Fz);
+                const int nf = s_tab[b].nbr[2], nk = s_tab[b].nbr[3];
+                if (nf >= 0) sP[b * vol + o] = sP[nf * vol + o + yE * sj];
+                if (nk >= 0) sP[b * vol + o + (yE + 2) * sj] = sP[nk * vol + o + 2 * sj];
+            }
+            __syncthreads();
+        }
+        if (wall_mode != FACE_NONE) {
+            const bool ng = (wall_mode == FACE_NEG_MIRROR);
+            for (int q = tid; q < nblk * Fy * Fz; q += nthr) {
+                const int b = q / (Fy * Fz), w = q % (Fy * Fz);
+                if (s_tab[b].wall[0]) { const double v = sP[b * vol + 2 * si + w]; sP[b * vol + w] = ng ? -v : v; }
+                if (s_tab[b].wall[1]) { const double v = sP[b * vol + xE * si + w]; sP[b * vol + (xE + 2) * si + w] = ng ? -v : v; }
+            }
+            __syncthreads();
+            if (DIM == 3) {
+                for (int q = tid; q < nblk * Fx * Fz; q += nthr) {
+                    const int b = q / (Fx * Fz), w = q % (Fx * Fz);
+                    const int o = b * vol + (w / Fz) * si + (w % Fz);
+                    if (s_tab[b].wall[2]) { const double v = sP[o + 2 * sj]; sP[o] = ng ? -v : v; }
+                    if (s_tab[b].wall[3]) { const double v = sP[o + yE * sj]; sP[o + (yE + 2) * sj] = ng ? -v : v; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int q = tid; q < nblk * Fx * Fy; q += nthr) {
+            const int o = q * Fz;                                   /* (b, i, j) row start */
+            if (z_lo_mode != FACE_NONE) {
+                const double v = sP[o + ((z_lo_mode == FACE_PERIODIC) ? zE : 2)];       /* k = zE-1 or k = 1 */
+                sP[o] = (z_lo_mode == FACE_NEG_MIRROR) ? -v : v;
+            }
+            if (z_hi_mode != FACE_NONE) {
+                const double v = sP[o + ((z_hi_mode == FACE_PERIODIC) ? 2 : zE)];
+                sP[o + zE + 2] = (z_hi_mode == FACE_NEG_MIRROR) ? -v : v;
+            }
+        }
+        __syncthreads();
+        if (iter < 0) break;
+
+        /* ---- block Gauss-Seidel wavefront ---- */
+        for (int h = 0; h < H; ++h) {
+            for (int q = tid; q < nblk * nij; q += nthr) {
+                const int b = q / nij, w = q % nij;
+                const int i = w / ny, j = w % ny, k = h - i - j;
+                if (k >= 0 && k < nz) {
+                    double *c = sP + b * vol + CS_AT(i, j, k);
+                    const int pt = b * cnt + (i * ny + j) * nz + k;
+                    double t;
+                    if (DIM == 3)
+                        t = relax3_num(c[si], c[-si], c[sj], c[-sj], c[1], c[-1], sR[b * vol + CS_AT(i, j, k)], cx2[b * nx + i], cx1[b * nx + i], hx,
+                                       cy2[b * ny + j], cy1[b * ny + j], hy, cz2[k], cz1[k], hz, two_h);
+                    else
+                        t = relax2_num(c[si], c[-si], c[1], c[-1], sR[b * vol + CS_AT(i, j, k)], cx2[b * nx + i], cx1[b * nx + i], hx, cz2[k], cz1[k], hz, two_h);
+                    c[0] = div_inv(t, sD[pt], sI[pt]);
+                }
+            }
+            __syncthreads();
+        }
+        double m = -1.0e-10;
+        for (int q = tid; q < nblk * cnt; q += nthr) {
+            const int b = q / cnt, w = q % cnt;
+            const int k = w % nz, j = (w / nz) % ny, i = w / (nz * ny);
+            const double *c = sP + b * vol + CS_AT(i, j, k);
+            const double r = sR[b * vol + CS_AT(i, j, k)];
+            double lp;
+            if (DIM == 3) {
+                lp = p2 ? lap3_inv<true>(c[0], c[si], c[-si], c[sj], c[-sj], c[1], c[-1], mx2[b * nx + i], mx1[b * nx + i], my2[b * ny + j], my1[b * ny + j], mz2[k], mz1[k], dv)
+                        : lap3_inv<false>(c[0], c[si], c[-si], c[sj], c[-sj], c[1], c[-1], mx2[b * nx + i], mx1[b * nx + i], my2[b * ny + j], my1[b * ny + j], mz2[k], mz1[k], dv);
+            } else {
+                lp = p2 ? lap2_inv<true>(c[0], c[si], c[-si], c[1], c[-1], mx2[b * nx + i], mx1[b * nx + i], mz2[k], mz1[k], dv)
+                        : lap2_inv<false>(c[0], c[si], c[-si], c[1], c[-1], mx2[b * nx + i], mx1[b * nx + i], mz2[k], mz1[k], dv);
+            }
+            m = fmax(m, fabs(r - lp));
+        }
+        m = block_reduce<true>(m, sm);
+        if (tid == 0) s_max = m;
+        __syncthreads();
+        const double gmax = s_max;
+        __syncthreads();
+        bool stop = gmax < tol;
+        if (!stop) { iter += 1; stop = iter > maxCount; }
+        if (stop) { if (tid == 0) *iters_out = iter; iter = -1; }
+    }
+    for (int q = tid; q < nblk * vol; q += nthr) {
+        const int b = q / vol, w = q % vol;
+        const int k = w % Fz - 1, j = (w / Fz) % Fy - jo, i = w / (Fz * Fy) - 1;
+        Pg[b * stride + mg_at(L, i, j, k)] = sP[q];
+    }
+#undef CS_AT
+}
+static inline size_t coarse_smem_bytes(const LevelView &L, int dim, int nblk) {
+    const size_t Fy = (dim == 2) ? 1 : L.Fy;
+    const size_t vol = (size_t)L.Fx * Fy * L.Fz, cnt = (size_t)L.nx * L.ny * L.nz;
+    return sizeof(double) * (nblk * (2 * vol + 2 * cnt) + 4 * (size_t)nblk * (L.nx + L.ny) + 4 * (size_t)L.nz + 16);
 }
 
 /* misc */

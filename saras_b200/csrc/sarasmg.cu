@@ -16,6 +16,7 @@
 #include "../../include/sarasmg.h"
 #include "mg_kernels.cuh"
 #include "gs_skew.cuh"
+#include "mg_tma.cuh"
 
 #include <nccl.h>
 
@@ -65,6 +66,9 @@ struct Level {
     int *gs_sync;
     size_t gs_smem;
     double *buf[3];         /* SARASMG_PRESSURE, SARASMG_RESIDUAL, SARASMG_TMP */
+    CUtensorMap tmapP[3];   /* TMA descriptors of the three arrays for the pressure box (with halo ring) ... */
+    CUtensorMap tmapR[3];   /* ... and for the right-hand-side box; swapped together with buf[] */
+    bool tma;               /* level is large enough for k_stencil_tma and the descriptors exist */
     double *met[6];         /* device metric arrays (padded, base -1) */
     size_t elems;           /* allocated doubles per array */
 };
@@ -203,92 +207,103 @@ static int copy_d2h(S *s, const Level &L, double *host, const double *dev) {
 /* ------------------------------------------------------------------------------------------------ */
 /* face operations                                                                                   */
 /* ------------------------------------------------------------------------------------------------ */
-static int launch_face(S *s, int dir, double *A, const Level &L, int lo, int hi, const double *wall) {
-    if (lo == FACE_NONE && hi == FACE_NONE) return 0;
+static int launch_faces(S *s, double *A, const Level &L, const int m[6], bool with_walls) {
+    bool any = false;
+    for (int q = 0; q < 6; q++) any = any || (m[q] != FACE_NONE);
+    if (!any) return 0;
+    FaceModes F;
+    for (int q = 0; q < 6; q++) F.m[q] = m[q];
+    if (s->planar) { F.m[2] = FACE_NONE; F.m[3] = FACE_NONE; }
+    F.xwall = with_walls ? s->d_wall[0] : nullptr; F.ywall = with_walls ? s->d_wall[1] : nullptr; F.zwall = with_walls ? s->d_wall[2] : nullptr;
     const LevelView &v = L.v;
-    const int nj = s->planar ? 1 : v.Fy;
-    if (dir == 0) {
-        k_face<0><<<face_blocks((long long)nj * v.Fz), 256, 0, s->st>>>(A, v, lo, hi, wall, s->planar);
-    } else if (dir == 1) {
-        if (s->planar) return 0;
-        k_face<1><<<face_blocks((long long)v.Fx * v.Fz), 256, 0, s->st>>>(A, v, lo, hi, wall, s->planar);
-    } else {
-        k_face<2><<<face_blocks((long long)v.Fx * nj), 256, 0, s->st>>>(A, v, lo, hi, wall, s->planar);
-    }
-    return kcheck(s, "k_face");
+    const long long nj = s->planar ? 1 : v.Fy;
+    const long long cnt = (long long)v.Fx * nj + (s->planar ? 0 : (long long)v.Fx * v.Fz) + nj * v.Fz;
+    if (s->planar) k_faces<2><<<face_blocks(cnt), 256, 0, s->st>>>(A, v, F);
+    else k_faces<3><<<face_blocks(cnt), 256, 0, s->st>>>(A, v, F);
+    return kcheck(s, "k_faces");
 }
 
 static int zero_pads(S *s, int level, double *A) {
     const Level &L = s->lev[level];
     ProfScope ps(s, SARASMG_K_MISC, level);
-    TRY(launch_face(s, 0, A, L, FACE_ZERO, FACE_ZERO, nullptr));
-    TRY(launch_face(s, 1, A, L, FACE_ZERO, FACE_ZERO, nullptr));
-    TRY(launch_face(s, 2, A, L, FACE_ZERO, FACE_ZERO, nullptr));
-    return 0;
+    const int m[6] = {FACE_ZERO, FACE_ZERO, FACE_ZERO, FACE_ZERO, FACE_ZERO, FACE_ZERO};
+    return launch_faces(s, A, L, m, false);
+}
+
+/* which x / y faces exchange with another rank, and which wrap onto this rank itself */
+struct PadPlan { bool rl, rr, rf, rb; int self[6]; bool any_remote, any_self; };
+static PadPlan pad_plan(const S *s) {
+    PadPlan p;
+    const int me = s->d.rank;
+    const int *fr = s->d.face_ranks;
+    for (int q = 0; q < 6; q++) p.self[q] = FACE_NONE;
+    p.rl = (fr[0] != SARASMG_PROC_NULL && fr[0] != me);
+    p.rr = (fr[1] != SARASMG_PROC_NULL && fr[1] != me);
+    p.rf = !s->planar && (fr[2] != SARASMG_PROC_NULL && fr[2] != me);
+    p.rb = !s->planar && (fr[3] != SARASMG_PROC_NULL && fr[3] != me);
+    if (fr[0] == me) p.self[0] = FACE_PERIODIC;           /* my i=-1 <- (self) i=xEnd-1 */
+    if (fr[1] == me) p.self[1] = FACE_PERIODIC;           /* my i=xEnd+1 <- (self) i=1 */
+    if (!s->planar && fr[2] == me) p.self[2] = FACE_PERIODIC;
+    if (!s->planar && fr[3] == me) p.self[3] = FACE_PERIODIC;
+    p.any_remote = p.rl || p.rr || p.rf || p.rb;
+    p.any_self = (p.self[0] | p.self[1] | p.self[2] | p.self[3]) != 0;
+    return p;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* updatePads (d3:671-686, d2:467-478).  x faces first, then y faces (which carry the fresh x pads):  */
 /* the program order of the reference's blocking self-sends, made deterministic for real neighbours.  */
-/* Neighbour == own rank (periodic, one rank along that axis): local copy kernel.                      */
+/* Neighbour == own rank (periodic, one rank along that axis): local copies (k_faces).                 */
 /* Neighbour == other rank: pack -> grouped ncclSend/ncclRecv -> unpack on the solver stream.          */
 /* ------------------------------------------------------------------------------------------------ */
 static int update_pads(S *s, int level, double *A) {
     const Level &L = s->lev[level];
     const LevelView &v = L.v;
-    const int me = s->d.rank;
     const int *fr = s->d.face_ranks;
+    const PadPlan pp = pad_plan(s);
     ProfScope ps(s, SARASMG_K_HALO, level);
+    if (!pp.any_remote) return launch_faces(s, A, L, pp.self, false);      /* x then y is the resolution order of k_faces */
+    if (!s->has_comm) return set_err("update_pads: remote neighbour but no NCCL communicator");
 
+    const int nj = s->planar ? 1 : v.Fy;
+    const long long cx = (long long)nj * v.Fz, cy = (long long)v.Fx * v.Fz;
     /* ---- x phase ---- */
-    {
-        const int lo = (fr[0] == me) ? FACE_PERIODIC : FACE_NONE;   /* my i=-1 <- (self) i=xEnd-1 */
-        const int hi = (fr[1] == me) ? FACE_PERIODIC : FACE_NONE;   /* my i=xEnd+1 <- (self) i=1 */
-        TRY(launch_face(s, 0, A, L, lo, hi, nullptr));
-        const bool rl = (fr[0] != SARASMG_PROC_NULL && fr[0] != me);
-        const bool rr = (fr[1] != SARASMG_PROC_NULL && fr[1] != me);
-        if (rl || rr) {
-            if (!s->has_comm) return set_err("update_pads: remote neighbour but no NCCL communicator");
-            const int nj = s->planar ? 1 : v.Fy;
-            const long long cnt = (long long)nj * v.Fz;
-            const unsigned nb = face_blocks(cnt);
-            if (rl) { k_pack_x<<<nb, 256, 0, s->st>>>(A, v, 1, s->planar, s->xs[0]); TRY(kcheck(s, "k_pack_x")); }
-            if (rr) { k_pack_x<<<nb, 256, 0, s->st>>>(A, v, v.nx - 2, s->planar, s->xs[1]); TRY(kcheck(s, "k_pack_x")); }
-            NC(ncclGroupStart());
-            /* order: (send left, recv right), (send right, recv left): keeps pairs matched when both neighbours are one peer */
-            if (rl) NC(ncclSend(s->xs[0], (size_t)cnt, ncclDouble, fr[0], s->comm, s->st));
-            if (rr) NC(ncclRecv(s->xr[1], (size_t)cnt, ncclDouble, fr[1], s->comm, s->st));
-            if (rr) NC(ncclSend(s->xs[1], (size_t)cnt, ncclDouble, fr[1], s->comm, s->st));
-            if (rl) NC(ncclRecv(s->xr[0], (size_t)cnt, ncclDouble, fr[0], s->comm, s->st));
-            NC(ncclGroupEnd());
-            if (rl) { k_unpack_x<<<nb, 256, 0, s->st>>>(A, v, -1, s->planar, s->xr[0]); TRY(kcheck(s, "k_unpack_x")); }
-            if (rr) { k_unpack_x<<<nb, 256, 0, s->st>>>(A, v, v.nx, s->planar, s->xr[1]); TRY(kcheck(s, "k_unpack_x")); }
-        }
+    if (pp.self[0] | pp.self[1]) {
+        const int m[6] = {pp.self[0], pp.self[1], FACE_NONE, FACE_NONE, FACE_NONE, FACE_NONE};
+        TRY(launch_faces(s, A, L, m, false));
     }
-    if (s->planar) return 0;
-
+    const bool xrem = pp.rl || pp.rr, yrem = pp.rf || pp.rb;
+    if (xrem) {
+        k_pack_x2<<<face_blocks(cx), 256, 0, s->st>>>(A, v, s->planar, pp.rl ? s->xs[0] : nullptr, pp.rr ? s->xs[1] : nullptr);
+        TRY(kcheck(s, "k_pack_x2"));
+        NC(ncclGroupStart());
+        /* order: (send left, recv right), (send right, recv left): keeps pairs matched when both neighbours are one peer */
+        if (pp.rl) NC(ncclSend(s->xs[0], (size_t)cx, ncclDouble, fr[0], s->comm, s->st));
+        if (pp.rr) NC(ncclRecv(s->xr[1], (size_t)cx, ncclDouble, fr[1], s->comm, s->st));
+        if (pp.rr) NC(ncclSend(s->xs[1], (size_t)cx, ncclDouble, fr[1], s->comm, s->st));
+        if (pp.rl) NC(ncclRecv(s->xr[0], (size_t)cx, ncclDouble, fr[0], s->comm, s->st));
+        NC(ncclGroupEnd());
+    }
+    /* ---- unpack x, pack y (one launch) ---- */
+    if (xrem || yrem) {
+        k_unpack_x_pack_y<<<face_blocks(cx + cy), 256, 0, s->st>>>(A, v, s->planar, pp.rl ? s->xr[0] : nullptr, pp.rr ? s->xr[1] : nullptr,
+                                                                   pp.rf ? s->ys[0] : nullptr, pp.rb ? s->ys[1] : nullptr);
+        TRY(kcheck(s, "k_unpack_x_pack_y"));
+    }
     /* ---- y phase ---- */
-    {
-        const int lo = (fr[2] == me) ? FACE_PERIODIC : FACE_NONE;
-        const int hi = (fr[3] == me) ? FACE_PERIODIC : FACE_NONE;
-        TRY(launch_face(s, 1, A, L, lo, hi, nullptr));
-        const bool rf = (fr[2] != SARASMG_PROC_NULL && fr[2] != me);
-        const bool rb = (fr[3] != SARASMG_PROC_NULL && fr[3] != me);
-        if (rf || rb) {
-            if (!s->has_comm) return set_err("update_pads: remote neighbour but no NCCL communicator");
-            const long long cnt = (long long)v.Fx * v.Fz;
-            const unsigned nb = face_blocks(cnt);
-            if (rf) { k_pack_y<<<nb, 256, 0, s->st>>>(A, v, 1, s->ys[0]); TRY(kcheck(s, "k_pack_y")); }
-            if (rb) { k_pack_y<<<nb, 256, 0, s->st>>>(A, v, v.ny - 2, s->ys[1]); TRY(kcheck(s, "k_pack_y")); }
-            NC(ncclGroupStart());
-            if (rf) NC(ncclSend(s->ys[0], (size_t)cnt, ncclDouble, fr[2], s->comm, s->st));
-            if (rb) NC(ncclRecv(s->yr[1], (size_t)cnt, ncclDouble, fr[3], s->comm, s->st));
-            if (rb) NC(ncclSend(s->ys[1], (size_t)cnt, ncclDouble, fr[3], s->comm, s->st));
-            if (rf) NC(ncclRecv(s->yr[0], (size_t)cnt, ncclDouble, fr[2], s->comm, s->st));
-            NC(ncclGroupEnd());
-            if (rf) { k_unpack_y<<<nb, 256, 0, s->st>>>(A, v, -1, s->yr[0]); TRY(kcheck(s, "k_unpack_y")); }
-            if (rb) { k_unpack_y<<<nb, 256, 0, s->st>>>(A, v, v.ny, s->yr[1]); TRY(kcheck(s, "k_unpack_y")); }
-        }
+    if (pp.self[2] | pp.self[3]) {
+        const int m[6] = {FACE_NONE, FACE_NONE, pp.self[2], pp.self[3], FACE_NONE, FACE_NONE};
+        TRY(launch_faces(s, A, L, m, false));
+    }
+    if (yrem) {
+        NC(ncclGroupStart());
+        if (pp.rf) NC(ncclSend(s->ys[0], (size_t)cy, ncclDouble, fr[2], s->comm, s->st));
+        if (pp.rb) NC(ncclRecv(s->yr[1], (size_t)cy, ncclDouble, fr[3], s->comm, s->st));
+        if (pp.rb) NC(ncclSend(s->ys[1], (size_t)cy, ncclDouble, fr[3], s->comm, s->st));
+        if (pp.rf) NC(ncclRecv(s->yr[0], (size_t)cy, ncclDouble, fr[2], s->comm, s->st));
+        NC(ncclGroupEnd());
+        k_unpack_y2<<<face_blocks(cy), 256, 0, s->st>>>(A, v, pp.rf ? s->yr[0] : nullptr, pp.rb ? s->yr[1] : nullptr);
+        TRY(kcheck(s, "k_unpack_y2"));
     }
     return 0;
 }
@@ -313,16 +328,82 @@ static void bc_modes(const S *s, int m[6]) {
 static int impose_bc(S *s, int level) {
     const Level &L = s->lev[level];
     double *P = L.buf[SARASMG_PRESSURE];
-    TRY(update_pads(s, level, P));
     int m[6];
     bc_modes(s, m);
-    if ((m[0] == FACE_WALL || m[2] == FACE_WALL || m[4] == FACE_WALL) && level != 0)
+    bool has_wall = false;
+    for (int q = 0; q < 6; q++) has_wall = has_wall || (m[q] == FACE_WALL);
+    if (has_wall && level != 0)
         return set_err("imposeBC: non-homogeneous Dirichlet BC requested on level %d (wall arrays exist on level 0 only)", level);
+    const PadPlan pp = pad_plan(s);
+    if (!pp.any_remote && !has_wall) {
+        /* one launch: without Dirichlet ghost values every operation is an index map (mirror / periodic copy, maybe negated),
+         * the maps of different axes commute, and the per-axis source resolution of k_faces gives exactly what the reference's
+         * x-pads, y-pads, x-wall, y-wall, z sequence leaves in every pad */
+        ProfScope ps(s, SARASMG_K_BC, level);
+        int all[6];
+        for (int q = 0; q < 6; q++) all[q] = (m[q] != FACE_NONE) ? m[q] : pp.self[q];     /* a wall BC is applied after, and over, the pad copy */
+        return launch_faces(s, P, L, all, false);
+    }
+    TRY(update_pads(s, level, P));
     ProfScope ps(s, SARASMG_K_BC, level);
-    TRY(launch_face(s, 0, P, L, m[0], m[1], s->d_wall[0]));
-    TRY(launch_face(s, 1, P, L, m[2], m[3], s->d_wall[1]));
-    TRY(launch_face(s, 2, P, L, m[4], m[5], s->d_wall[2]));
+    return launch_faces(s, P, L, m, true);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* TMA descriptors of a level array (mg_tma.cuh): 3-D fp64 tensor [pitch, Fy, Fx], dense box, zero OOB fill */
+/* ------------------------------------------------------------------------------------------------ */
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+static int make_level_tmaps(S *s, Level &L) {
+    L.tma = false;
+    const LevelView &v = L.v;
+    if (s->planar || getenv("SARASMG_NO_TMA")) return 0;
+    if (const char *e = getenv("SARASMG_TMA_MIN")) {            /* tests: force the TMA kernels onto small levels */
+        const int m = atoi(e);
+        if (v.nx < m || v.ny < m || v.nz < m) return 0;
+    } else if (v.nz < 257 || v.ny < 65 || v.nx < 65) return 0;  /* below this the tile ring does not pay; register-marching kernels */
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) return set_err("cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)v.pitch, (cuuint64_t)v.Fy, (cuuint64_t)v.Fx};
+    const cuuint64_t strides[2] = {(cuuint64_t)v.pitch * sizeof(double), (cuuint64_t)v.plane * sizeof(double)};
+    const cuuint32_t boxP[3] = {MG_TMA_TZ + 4, MG_TMA_TY + 2, 1}, boxR[3] = {MG_TMA_TZ, MG_TMA_TY, 1}, es[3] = {1, 1, 1};
+    for (int a = 0; a < 3; a++) {
+        CUresult r1 = enc(&L.tmapP[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, L.buf[a], dims, strides, boxP, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r2 = enc(&L.tmapR[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, L.buf[a], dims, strides, boxR, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return set_err("cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+    }
+    L.tma = true;
     return 0;
+}
+struct TmaGeom { dim3 grid, block; int ichunk; };
+static TmaGeom tma_geom(const LevelView &v) {
+    TmaGeom g;
+    g.block = dim3(MG_TMA_TZ / 2, MG_TMA_TY / 2, 1);      /* a thread owns a z pair of two adjacent rows */
+    const unsigned gx = cdiv(v.nz, MG_TMA_TZ), gy = cdiv(v.ny, MG_TMA_TY);
+    /* x chunks: enough CTAs for ~8 waves of 2 CTAs on 148 SMs, as few as possible otherwise (each chunk re-reads 2 planes) */
+    int nch = (int)cdiv(148LL * 2 * 8, (long long)gx * gy);
+    nch = std::max(1, std::min(nch, v.nx / 8));
+    nch = std::max(nch, (v.nx + MG_TMA_MAXCH - 1) / MG_TMA_MAXCH);     /* the kernel's x-coefficient table holds MG_TMA_MAXCH planes */
+    g.ichunk = (v.nx + nch - 1) / nch;
+    g.grid = dim3(gx, gy, cdiv(v.nx, g.ichunk));
+    return g;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -446,7 +527,11 @@ static int op_smooth(S *s, int count) {
             } else {
                 const MarchGeom g = march_geom(s, L.v);
                 double *P = L.buf[SARASMG_PRESSURE], *R = L.buf[SARASMG_RESIDUAL], *T = L.buf[SARASMG_TMP];
-                if (s->planar) {
+                if (L.tma) {
+                    const TmaGeom t = tma_geom(L.v);
+                    if (L.x_uniform) k_stencil_tma<0, true><<<t.grid, t.block, MG_TMA_SMEM, s->st>>>(L.tmapP[SARASMG_PRESSURE], L.tmapR[SARASMG_RESIDUAL], T, L.v, t.ichunk, 0, 0.0, 0.0, 0.0, nullptr, 0);
+                    else k_stencil_tma<0, false><<<t.grid, t.block, MG_TMA_SMEM, s->st>>>(L.tmapP[SARASMG_PRESSURE], L.tmapR[SARASMG_RESIDUAL], T, L.v, t.ichunk, 0, 0.0, 0.0, 0.0, nullptr, 0);
+                } else if (s->planar) {
                     if (L.x_uniform) k_stencil_march<2, 0, true><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
                     else k_stencil_march<2, 0, false><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
                 } else {
@@ -455,6 +540,8 @@ static int op_smooth(S *s, int count) {
                 }
                 TRY(kcheck(s, "k_stencil_march<jacobi>"));
                 std::swap(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_TMP]);      /* d3:168 */
+                std::swap(L.tmapP[SARASMG_PRESSURE], L.tmapP[SARASMG_TMP]);
+                std::swap(L.tmapR[SARASMG_PRESSURE], L.tmapR[SARASMG_TMP]);
             }
         }
         s->bucket = 0;
@@ -475,7 +562,11 @@ static int op_compute_residual(S *s) {
         const MarchGeom g = march_geom(s, L.v);
         double *P = L.buf[SARASMG_PRESSURE], *R = L.buf[SARASMG_RESIDUAL], *T = L.buf[SARASMG_TMP];
         const bool p2 = divisors_pow2(s->planar, L.v.hx * L.v.hx, L.v.hx, L.v.hy, L.v.hz * L.v.hz, L.v.hz) && !s->no_pow2;
-        if (s->planar) {
+        if (L.tma) {
+            const TmaGeom t = tma_geom(L.v);
+            if (p2) k_stencil_tma<1, true><<<t.grid, t.block, MG_TMA_SMEM, s->st>>>(L.tmapP[SARASMG_PRESSURE], L.tmapR[SARASMG_RESIDUAL], T, L.v, t.ichunk, 0, 0.0, 0.0, 0.0, nullptr, 0);
+            else k_stencil_tma<1, false><<<t.grid, t.block, MG_TMA_SMEM, s->st>>>(L.tmapP[SARASMG_PRESSURE], L.tmapR[SARASMG_RESIDUAL], T, L.v, t.ichunk, 0, 0.0, 0.0, 0.0, nullptr, 0);
+        } else if (s->planar) {
             if (p2) k_stencil_march<2, 1, true><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
             else k_stencil_march<2, 1, false><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk);
         } else {
@@ -569,7 +660,8 @@ static int op_compute_error(S *s, int norm, double *value) {
     if (norm != 1 && norm != 2) return 0;           /* resType 0: returns 0 (d3:392,418) */
     Level &L = s->lev[0];
     const MarchGeom g = march_geom(s, L.v);
-    const int nb = g.grid.x * g.grid.y * g.grid.z;
+    const TmaGeom tg = tma_geom(L.v);
+    const int nb = L.tma ? tg.grid.x * tg.grid.y * tg.grid.z : g.grid.x * g.grid.y * g.grid.z;
     TRY(ensure_part(s, (size_t)2 * nb + 4096));
     {
         ProfScope ps(s, SARASMG_K_ERROR, 0);
@@ -579,6 +671,10 @@ static int op_compute_error(S *s, int norm, double *value) {
             const bool p2 = divisors_pow2(true, L.v.hx2, L.v.hx, 0.0, L.v.hz2, L.v.hz) && !s->no_pow2;
             if (p2) k_error_march<2, true><<<g.grid, g.block, 0, s->st>>>(P, R, L.v, g.ichunk, norm, L.v.hx, L.v.hy, L.v.hz, s->d_part, nb);
             else k_error_march<2, false><<<g.grid, g.block, 0, s->st>>>(P, R, L.v, g.ichunk, norm, L.v.hx, L.v.hy, L.v.hz, s->d_part, nb);
+        } else if (L.tma) {
+            const bool p2 = divisors_pow2(false, Lv.v.hx * Lv.v.hx, Lv.v.hx, Lv.v.hy, Lv.v.hz * Lv.v.hz, Lv.v.hz) && !s->no_pow2;
+            if (p2) k_stencil_tma<2, true><<<tg.grid, tg.block, MG_TMA_SMEM, s->st>>>(L.tmapP[SARASMG_PRESSURE], L.tmapR[SARASMG_RESIDUAL], nullptr, L.v, tg.ichunk, norm, Lv.v.hx, Lv.v.hy, Lv.v.hz, s->d_part, nb);
+            else k_stencil_tma<2, false><<<tg.grid, tg.block, MG_TMA_SMEM, s->st>>>(L.tmapP[SARASMG_PRESSURE], L.tmapR[SARASMG_RESIDUAL], nullptr, L.v, tg.ichunk, norm, Lv.v.hx, Lv.v.hy, Lv.v.hz, s->d_part, nb);
         } else {
             const bool p2 = divisors_pow2(false, Lv.v.hx * Lv.v.hx, Lv.v.hx, Lv.v.hy, Lv.v.hz * Lv.v.hz, Lv.v.hz) && !s->no_pow2;
             if (p2) k_error_march<3, true><<<g.grid, g.block, 0, s->st>>>(P, R, L.v, g.ichunk, norm, Lv.v.hx, Lv.v.hy, Lv.v.hz, s->d_part, nb);
@@ -635,6 +731,19 @@ static int setup_agglomeration(S *s) {
     if (np > 16 || s->D == 0) return 0;                 /* table size of the kernel; D == 0 would need every rank's wall planes */
     Level &L = s->lev[s->D];
     const LevelView &v = L.v;
+    if (np == 1) {                                      /* single rank: a one-entry table over the level's own arrays */
+        int m1[6];
+        bc_modes(s, m1);
+        CoarseBlock cb;
+        for (int f = 0; f < 4; f++) { cb.nbr[f] = (d.face_ranks[f] == d.rank) ? 0 : -1; cb.wall[f] = (m1[f] != FACE_NONE) ? 1 : 0; }
+        if (s->planar) { cb.nbr[2] = cb.nbr[3] = -1; cb.wall[2] = cb.wall[3] = 0; }
+        cb.xixx = v.xixx; cb.xix2 = v.xix2; cb.etyy = v.etyy; cb.ety2 = v.ety2;
+        CU(cudaMalloc(&s->agg_tab, sizeof(CoarseBlock)));
+        CU(cudaMemcpyAsync(s->agg_tab, &cb, sizeof(CoarseBlock), cudaMemcpyHostToDevice, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        s->agg_ok = true;
+        return 0;
+    }
     const int mx = v.Fx + 2, my = v.Fy + 2;
     const int rec = 8 + 2 * mx + 2 * my;                /* doubles per rank: 4 neighbours, 4 wall flags, xixx, xix2, etyy, ety2 */
     std::vector<double> mine(rec, 0.0), all((size_t)rec * np, 0.0);
@@ -686,14 +795,36 @@ static int op_solve_coarsest(S *s, int *iters, bool sync) {
     bool remote = false;
     for (int f = 0; f < 4; f++) if (fr[f] != SARASMG_PROC_NULL && fr[f] != d.rank) remote = true;
     ProfScope ps(s, SARASMG_K_COARSE_SOLVE, l);
-    if (d.n_proc == 1 || (!remote && !s->has_comm)) {
-        BcPlan B;
-        bc_plan(s, B);
-        if ((B.bc_x_lo == FACE_WALL || B.bc_y_lo == FACE_WALL || B.bc_z_lo == FACE_WALL) && l != 0)
-            return set_err("solve: non-homogeneous Dirichlet BC on level %d", l);
-        if (s->planar) k_coarse_solve<2><<<1, 1024, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, B, d.mg_tolerance, s->maxCount, s->d_iters);
-        else k_coarse_solve<3><<<1, 1024, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, B, d.mg_tolerance, s->maxCount, s->d_iters);
-        TRY(kcheck(s, "k_coarse_solve"));
+    if (s->agg_ok && !s->coarse_legacy && l == s->D) {
+        /* the whole while(true) of solve() in one CTA.  Several ranks: all-gather the coarsest arrays once and replay all
+         * rank-blocks on every rank (k_coarse_solve_blocks / _smem); one rank: the same kernel over the level's own arrays */
+        int m[6];
+        bc_modes(s, m);
+        const int wall = d.test_poisson ? (s->zeroBC ? FACE_NEG_MIRROR : FACE_WALL) : FACE_MIRROR;
+        if (wall == FACE_WALL) return set_err("solve: non-homogeneous Dirichlet BC on level %d", l);
+        const int nblk = d.n_proc;
+        double *Pa = L.buf[SARASMG_PRESSURE];
+        const double *Ra = L.buf[SARASMG_RESIDUAL];
+        if (nblk > 1) {
+            NC(ncclGroupStart());
+            NC(ncclAllGather(L.buf[SARASMG_PRESSURE], s->agg_P, L.elems, ncclDouble, s->comm, s->st));
+            NC(ncclAllGather(L.buf[SARASMG_RESIDUAL], s->agg_R, L.elems, ncclDouble, s->comm, s->st));
+            NC(ncclGroupEnd());
+            Pa = s->agg_P; Ra = s->agg_R;
+        }
+        const size_t smem = coarse_smem_bytes(L.v, d.dim, nblk);
+        const int p2 = (divisors_pow2(s->planar, L.v.hx * L.v.hx, L.v.hx, L.v.hy, L.v.hz * L.v.hz, L.v.hz) && !s->no_pow2) ? 1 : 0;
+        if (smem <= 200 * 1024 && !getenv("SARASMG_COARSE_GLOBAL")) {
+            if (s->planar) k_coarse_solve_smem<2><<<1, 256, smem, s->st>>>(Pa, Ra, (long long)L.elems, nblk, s->agg_tab, L.v, wall, m[4], m[5], p2, d.mg_tolerance, s->maxCount, s->d_iters);
+            else k_coarse_solve_smem<3><<<1, 256, smem, s->st>>>(Pa, Ra, (long long)L.elems, nblk, s->agg_tab, L.v, wall, m[4], m[5], p2, d.mg_tolerance, s->maxCount, s->d_iters);
+            TRY(kcheck(s, "k_coarse_solve_smem"));
+        } else {
+            if (s->planar) k_coarse_solve_blocks<2><<<1, 1024, 0, s->st>>>(Pa, Ra, (long long)L.elems, nblk, s->agg_tab, L.v, wall, m[4], m[5], d.mg_tolerance, s->maxCount, s->d_iters);
+            else k_coarse_solve_blocks<3><<<1, 1024, 0, s->st>>>(Pa, Ra, (long long)L.elems, nblk, s->agg_tab, L.v, wall, m[4], m[5], d.mg_tolerance, s->maxCount, s->d_iters);
+            TRY(kcheck(s, "k_coarse_solve_blocks"));
+        }
+        if (nblk > 1)
+            CU(cudaMemcpyAsync(L.buf[SARASMG_PRESSURE], s->agg_P + (size_t)d.rank * L.elems, L.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
         CU(cudaMemcpyAsync(s->h_iters, s->d_iters, sizeof(int), cudaMemcpyDeviceToHost, s->st));
         if (sync) {
             CU(cudaStreamSynchronize(s->st));
@@ -702,20 +833,14 @@ static int op_solve_coarsest(S *s, int *iters, bool sync) {
         }
         return 0;
     }
-    if (s->agg_ok && !s->coarse_legacy && l == s->D) {
-        /* several ranks, agglomerated: all-gather the coarsest arrays once, replay all rank-blocks in one CTA on every rank */
-        int m[6];
-        bc_modes(s, m);
-        const int wall = d.test_poisson ? (s->zeroBC ? FACE_NEG_MIRROR : FACE_WALL) : FACE_MIRROR;
-        if (wall == FACE_WALL) return set_err("solve: non-homogeneous Dirichlet BC on level %d", l);
-        NC(ncclGroupStart());
-        NC(ncclAllGather(L.buf[SARASMG_PRESSURE], s->agg_P, L.elems, ncclDouble, s->comm, s->st));
-        NC(ncclAllGather(L.buf[SARASMG_RESIDUAL], s->agg_R, L.elems, ncclDouble, s->comm, s->st));
-        NC(ncclGroupEnd());
-        if (s->planar) k_coarse_solve_blocks<2><<<1, 1024, 0, s->st>>>(s->agg_P, s->agg_R, (long long)L.elems, d.n_proc, s->agg_tab, L.v, wall, m[4], m[5], d.mg_tolerance, s->maxCount, s->d_iters);
-        else k_coarse_solve_blocks<3><<<1, 1024, 0, s->st>>>(s->agg_P, s->agg_R, (long long)L.elems, d.n_proc, s->agg_tab, L.v, wall, m[4], m[5], d.mg_tolerance, s->maxCount, s->d_iters);
-        TRY(kcheck(s, "k_coarse_solve_blocks"));
-        CU(cudaMemcpyAsync(L.buf[SARASMG_PRESSURE], s->agg_P + (size_t)d.rank * L.elems, L.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->st));
+    if (d.n_proc == 1 || (!remote && !s->has_comm)) {
+        BcPlan B;
+        bc_plan(s, B);
+        if ((B.bc_x_lo == FACE_WALL || B.bc_y_lo == FACE_WALL || B.bc_z_lo == FACE_WALL) && l != 0)
+            return set_err("solve: non-homogeneous Dirichlet BC on level %d", l);
+        if (s->planar) k_coarse_solve<2><<<1, 1024, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, B, d.mg_tolerance, s->maxCount, s->d_iters);
+        else k_coarse_solve<3><<<1, 1024, 0, s->st>>>(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_RESIDUAL], L.v, B, d.mg_tolerance, s->maxCount, s->d_iters);
+        TRY(kcheck(s, "k_coarse_solve"));
         CU(cudaMemcpyAsync(s->h_iters, s->d_iters, sizeof(int), cudaMemcpyDeviceToHost, s->st));
         if (sync) {
             CU(cudaStreamSynchronize(s->st));
@@ -991,6 +1116,15 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
         v.xixx = L.met[0] + 1; v.xix2 = L.met[1] + 1; v.etyy = L.met[2] + 1; v.ety2 = L.met[3] + 1; v.ztzz = L.met[4] + 1; v.ztz2 = L.met[5] + 1;
     }
     for (int l = 0; l <= D; l++) TRY(build_gs_plan(s, s->lev[l]));
+    for (int l = 0; l <= D; l++) TRY(make_level_tmaps(s, s->lev[l]));
+    CU(cudaFuncSetAttribute(k_coarse_solve_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_coarse_solve_smem<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_stencil_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
+    CU(cudaFuncSetAttribute(k_stencil_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
+    CU(cudaFuncSetAttribute(k_stencil_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
+    CU(cudaFuncSetAttribute(k_stencil_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
+    CU(cudaFuncSetAttribute(k_stencil_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
+    CU(cudaFuncSetAttribute(k_stencil_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
     CU(cudaFuncSetAttribute(k_gs_skew<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_gs_skew<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {   /* p:360-361 maxCount */
@@ -1034,6 +1168,7 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
         CU(cudaMalloc(&s->d_gather, (size_t)desc->n_proc * 8 * sizeof(double)));
         TRY(setup_agglomeration(s));
     }
+    if (desc->n_proc == 1) TRY(setup_agglomeration(s));
     s->d.nccl_id = nullptr;     /* the caller's buffers are not retained */
     s->d.hx = s->d.hy = s->d.hz = s->d.hx2 = s->d.hz2 = s->d.hzhx = s->d.hxhy = s->d.hyhz = s->d.hxhyhz = nullptr;
     s->d.xixx = s->d.xix2 = s->d.etyy = s->d.ety2 = s->d.ztzz = s->d.ztz2 = nullptr;

@@ -46,8 +46,13 @@ def _load_both(o, s, level, which, arr):
 
 
 @pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
-@pytest.mark.parametrize("gs", [0, 1], ids=["jacobi", "gs"])
-def test_smooth_bitexact(case, gs):
+@pytest.mark.parametrize("gs", [0, 1, 2], ids=["jacobi", "gs", "jacobi_tma"])
+def test_smooth_bitexact(case, gs, monkeypatch):
+    if gs == 2:
+        if case["dim"] == 2:
+            pytest.skip("the TMA kernels are 3-D only")
+        _select_path(monkeypatch, "tma")
+        gs = 0
     o, s = _mk(case, gsSmooth=gs)
     for level in range(o.depth + 1):
         _, F = o.level_dims(level)
@@ -70,11 +75,19 @@ def _select_path(monkeypatch, path):
     if path == "general":
         monkeypatch.setenv("SARASMG_NO_POW2", "1")
         monkeypatch.setenv("SARASMG_PROLONG_LEGACY", "1")
+    if path in ("tma", "tma_general"):
+        # the TMA-staged marching kernels normally serve levels with nz >= 257; force them onto these small grids, where
+        # almost every tile hangs over the array edge (zero-filled by the hardware, masked in the kernel)
+        monkeypatch.setenv("SARASMG_TMA_MIN", "3")
+    if path == "tma_general":
+        monkeypatch.setenv("SARASMG_NO_POW2", "1")
 
 
 @pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
-@pytest.mark.parametrize("path", ["fast", "general"])
+@pytest.mark.parametrize("path", ["fast", "general", "tma", "tma_general"])
 def test_residual_coarsen_prolong_bitexact(case, path, monkeypatch):
+    if path.startswith("tma") and case["dim"] == 2:
+        pytest.skip("the TMA kernels are 3-D only")
     _select_path(monkeypatch, path)
     o, s = _mk(case)
     for level in range(o.depth):
@@ -136,8 +149,10 @@ def test_solve_coarsest_bitexact(case):
 
 @pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
 @pytest.mark.parametrize("norm", [1, 2])
-@pytest.mark.parametrize("path", ["fast", "general"])
+@pytest.mark.parametrize("path", ["fast", "general", "tma", "tma_general"])
 def test_compute_error(case, norm, path, monkeypatch):
+    if path.startswith("tma") and case["dim"] == 2:
+        pytest.skip("the TMA kernels are 3-D only")
     _select_path(monkeypatch, path)
     o, s = _mk(case)
     _, F = o.level_dims(0)
@@ -154,8 +169,13 @@ def test_compute_error(case, norm, path, monkeypatch):
 
 
 @pytest.mark.parametrize("case", ALL, ids=lambda c: c["name"])
-@pytest.mark.parametrize("gs", [0, 1], ids=["jacobi", "gs"])
-def test_vcycle_bitexact(case, gs):
+@pytest.mark.parametrize("gs", [0, 1, 2], ids=["jacobi", "gs", "jacobi_tma"])
+def test_vcycle_bitexact(case, gs, monkeypatch):
+    if gs == 2:
+        if case["dim"] == 2:
+            pytest.skip("the TMA kernels are 3-D only")
+        _select_path(monkeypatch, "tma")
+        gs = 0
     o, s = _mk(case, gsSmooth=gs)
     _, F = o.level_dims(0)
     rhs = smooth_rhs(o, 0, F) if not case.get("test_poisson") else np.ones(F)
@@ -255,4 +275,27 @@ def test_persistent_hierarchy_repeat_solves():
         s.mg_solve(p, rhs)
         outs.append(p)
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
+    s.close()
+
+
+@pytest.mark.parametrize("mesh", ["uniform", "tanh"])
+def test_tma_kernels_multi_tile_bitexact(mesh, monkeypatch):
+    """k_stencil_tma at its production tile shape: 65 x 65 x 257 spans 3 z tiles, 9 y tiles and several x chunks, so
+    interior tiles, edge tiles and chunk seams are all exercised (Jacobi sweeps, residual, error norm) against the oracle."""
+    monkeypatch.setenv("SARASMG_TMA_MIN", "65")
+    kw = dict(xGrid=2, yGrid=2, zGrid=2, betaX=1.2, betaY=0.9, betaZ=1.4) if mesh == "tanh" else {}
+    o, s = _mk(dict(name="tma_mid", dim=3, xInd=6, yInd=6, zInd=8, vcDepth=2, gsSmooth=0, **kw))
+    _, F = o.level_dims(0)
+    _load_both(o, s, 0, mo.PRESSURE, seeded_field(F, 200))
+    _load_both(o, s, 0, mo.RESIDUAL, seeded_field(F, 201, 4.0))
+    o.set_level(0); s.set_level(0)
+    o.smooth(3); s.smooth(3)
+    assert np.array_equal(s.level_get(0, capi.PRESSURE), o.array(0, 0, mo.PRESSURE))
+    o.compute_residual(); s.compute_residual()
+    assert np.array_equal(s.level_get(0, capi.TMP), o.array(0, 0, mo.TMP))
+    assert s.compute_error(1) == o.compute_error(1)
+    a, b = s.compute_error(2), o.compute_error(2)
+    assert abs(a - b) <= 1e-13 * abs(b)
+    o.vcycle(); s.vcycle()
+    assert np.array_equal(s.level_get(0, capi.PRESSURE), o.array(0, 0, mo.PRESSURE))
     s.close()
