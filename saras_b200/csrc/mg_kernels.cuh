@@ -215,6 +215,9 @@ __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<do
 #ifndef MG_PF_DIST
 #define MG_PF_DIST 0
 #endif
+#ifndef MG_PROLONG_PF
+#define MG_PROLONG_PF 0
+#endif
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int DIM, int MODE /* 0 Jacobi, 1 residual */, bool XU /* MODE 0: xix2 constant on this level, the Jacobi diagonal is march-invariant;
                                                                  MODE 1: the six divisors are powers of two (div_by) */>
@@ -446,6 +449,83 @@ __global__ void __launch_bounds__(256) k_sub_scalar_padded(double *__restrict__ 
     for (long long rrow = blockIdx.x; rrow < rows; rrow += gridDim.x) {
         double *a = A + rrow * L.pitch + MG_LEAD;
         for (int k = threadIdx.x; k < L.Fz; k += blockDim.x) a[k] = a[k] - v;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* mgSolve preamble (p:107-128) in three streaming passes instead of memset x2 + copy x2 + reduce + sub:  */
+/*   k_load_inputs   pressureData(0) / residualData(0) = 0 everywhere, core = core of inFn / rhs (p:107-115),   */
+/*                   and the sum of the rhs core (first part of blitz::mean, p:122), 32 B per point;       */
+/*   k_reduce_shell  sum of the pads of residualData(0) after updatePads (the rest of that mean);          */
+/*   k_sub_rows      residualData(0) -= globalAvg over the whole padded array (p:128), 16 B per point.      */
+/* Rows are walked with aligned 128-bit accesses: column c of a row holds k = c - (MG_LEAD + 1).            */
+/* ------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) k_load_inputs(const double *__restrict__ inP, const double *__restrict__ inR,
+                                                     double *__restrict__ P, double *__restrict__ R, const LevelView L,
+                                                     double *__restrict__ part) {
+    __shared__ double sm[32];
+    const long long rows = (long long)L.Fx * L.Fy;
+    const int npair = L.pitch / 2;
+    double acc = 0.0;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int i = (int)(row / L.Fy) - 1, j = (int)(row % L.Fy) - 1;
+        const bool core_row = (i >= 0 && i < L.nx && j >= 0 && j < L.ny);
+        const long long base = row * L.pitch;
+        for (int q = threadIdx.x; q < npair; q += blockDim.x) {
+            const int k = 2 * q - (MG_LEAD + 1);
+            double2 p = make_double2(0.0, 0.0), r = make_double2(0.0, 0.0);
+            if (core_row && k + 1 >= 0 && k < L.nz) {
+                const double2 a = ld2(inP + base + 2 * q), b = ld2(inR + base + 2 * q);
+                if (k >= 0) { p.x = a.x; r.x = b.x; acc += b.x; }
+                if (k + 1 < L.nz) { p.y = a.y; r.y = b.y; acc += b.y; }
+            }
+            st2(P + base + 2 * q, p);
+            st2(R + base + 2 * q, r);
+        }
+    }
+    acc = block_reduce<false>(acc, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+/* sum over the pad shell of a level array: x-pad planes, y-pad rows of the core planes, z-pad ends of the core rows */
+__global__ void __launch_bounds__(256) k_reduce_shell(const double *__restrict__ A, const LevelView L, double *__restrict__ part) {
+    __shared__ double sm[32];
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    const long long nXp = 2LL * L.Fy * L.Fz;                    /* planes i = -1, nx: every (j, k) */
+    const long long nYp = 2LL * L.nx * L.Fz;                    /* rows j = -1, ny of the core planes: every k */
+    const long long nZp = 2LL * L.nx * L.ny;                    /* k = -1, nz of the core rows */
+    double acc = 0.0;
+    for (long long q = tid; q < nXp + nYp + nZp; q += nthr) {
+        int i, j, k;
+        if (q < nXp) {
+            const long long w = q % ((long long)L.Fy * L.Fz);
+            i = (q < (long long)L.Fy * L.Fz) ? -1 : L.nx; j = (int)(w / L.Fz) - 1; k = (int)(w % L.Fz) - 1;
+        } else if (q < nXp + nYp) {
+            const long long w = q - nXp, h = (long long)L.nx * L.Fz;
+            j = (w < h) ? -1 : L.ny; i = (int)((w % h) / L.Fz); k = (int)(w % L.Fz) - 1;
+        } else {
+            const long long w = q - nXp - nYp, h = (long long)L.nx * L.ny;
+            k = (w < h) ? -1 : L.nz; i = (int)((w % h) / L.ny); j = (int)(w % L.ny);
+        }
+        acc += A[mg_at(L, i, j, k)];
+    }
+    acc = block_reduce<false>(acc, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_sub_rows(double *__restrict__ A, const LevelView L, const double v) {
+    const long long rows = (long long)L.Fx * L.Fy;
+    const int npair = L.pitch / 2;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long base = row * L.pitch;
+        for (int q = threadIdx.x; q < npair; q += blockDim.x) {
+            const int k = 2 * q - (MG_LEAD + 1);                /* the padded array covers k = -1 .. nz */
+            if (k + 1 < -1 || k > L.nz) continue;
+            double2 a = ld2(A + base + 2 * q);
+            if (k >= -1) a.x = a.x - v;
+            if (k + 1 <= L.nz) a.y = a.y - v;
+            st2(A + base + 2 * q, a);
+        }
     }
 }
 
@@ -844,6 +924,11 @@ __global__ void __launch_bounds__(256) k_prolong_march(const double *__restrict_
         }
         double *fe = f + (long long)(2 * i2 + 1) * Lf.plane;         /* fine plane 2*i2 */
         double *fo = fe + Lf.plane;                                   /* fine plane 2*i2+1 */
+        if (MG_PROLONG_PF > 0 && i2 + MG_PROLONG_PF < i1) {           /* ask L2 for the fine rows of a later step */
+            const double *g = fe + (long long)(2 * MG_PROLONG_PF) * Lf.plane;
+            prefetch_l2(g); prefetch_l2(g + Lf.plane);
+            if (hj) { prefetch_l2(g + fp); prefetch_l2(g + Lf.plane + fp); }
+        }
         /* even i */
         {
             double2 v;

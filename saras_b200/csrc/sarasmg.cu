@@ -913,39 +913,41 @@ static int solve_core(S *s, const double *in_p, const double *in_rhs, int *cycle
     const sarasmg_desc &d = s->d;
     Level &L0 = s->lev[0];
     s->vLevel = 0;
-    /* p:107-111: zero the hierarchy (smoothedPres has no storage; tmpDataArray is not zeroed here either) */
-    for (int l = 0; l <= s->D; l++) {
+    /* p:107-115: zero the hierarchy, load the cores of rhs / inFn into level 0 (one fused pass over level 0) */
+    for (int l = 1; l <= s->D; l++) {
         Level &L = s->lev[l];
         CU(cudaMemsetAsync(L.buf[SARASMG_PRESSURE], 0, L.elems * sizeof(double), s->st));
         CU(cudaMemsetAsync(L.buf[SARASMG_RESIDUAL], 0, L.elems * sizeof(double), s->st));
     }
-    /* p:114-115: core of rhs -> residualData(0), core of inFn -> pressureData(0) */
+    const unsigned nbp = std::min(cdiv((long long)L0.v.Fx * L0.v.Fy, 2), 148u * 16u);
+    TRY(ensure_part(s, 2 * (size_t)nbp + 4096));
     {
-        dim3 grid(cdiv(L0.v.nz, 128), L0.v.ny, L0.v.nx);
-        k_copy_core<<<grid, 128, 0, s->st>>>(in_rhs, L0.buf[SARASMG_RESIDUAL], L0.v);
-        TRY(kcheck(s, "k_copy_core"));
-        k_copy_core<<<grid, 128, 0, s->st>>>(in_p, L0.buf[SARASMG_PRESSURE], L0.v);
-        TRY(kcheck(s, "k_copy_core"));
+        ProfScope ps(s, SARASMG_K_MISC, 0);
+        k_load_inputs<<<nbp, 256, 0, s->st>>>(in_p, in_rhs, L0.buf[SARASMG_PRESSURE], L0.buf[SARASMG_RESIDUAL], L0.v, s->d_part);
+        TRY(kcheck(s, "k_load_inputs"));
+        k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part, (int)nbp, 1, 0u, s->d_scal);      /* d_scal[0] = sum of the rhs core */
+        TRY(kcheck(s, "k_reduce_final"));
     }
     TRY(update_pads(s, 0, L0.buf[SARASMG_RESIDUAL]));       /* p:117 */
     TRY(update_pads(s, 0, L0.buf[SARASMG_PRESSURE]));       /* p:118 */
 
     if (!d.test_poisson) {                                  /* p:120-129 */
-        const unsigned nbp = std::min(cdiv((long long)L0.v.Fx * L0.v.Fy, 4), 2048u);
-        TRY(ensure_part(s, nbp));
-        k_reduce_padded<0><<<nbp, 256, 0, s->st>>>(L0.buf[SARASMG_RESIDUAL], L0.v, s->d_part);
-        TRY(kcheck(s, "k_reduce_padded"));
-        k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part, (int)nbp, 1, 0u, s->d_scal);
+        ProfScope ps(s, SARASMG_K_MISC, 0);
+        const long long shell = 2LL * L0.v.Fy * L0.v.Fz + 2LL * L0.v.nx * L0.v.Fz + 2LL * L0.v.nx * L0.v.ny;
+        const unsigned nbs = std::min(cdiv(shell, 256), 1024u);
+        k_reduce_shell<<<nbs, 256, 0, s->st>>>(L0.buf[SARASMG_RESIDUAL], L0.v, s->d_part + nbp);
+        TRY(kcheck(s, "k_reduce_shell"));
+        k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part + nbp, (int)nbs, 1, 0u, s->d_scal + 1);   /* d_scal[1] = sum of the pads */
         TRY(kcheck(s, "k_reduce_final"));
         std::vector<double> sums;
-        TRY(gather_scalars(s, 1, sums));
+        TRY(gather_scalars(s, 2, sums));
         const double cnt = (double)((long long)L0.v.Fx * L0.v.Fy * L0.v.Fz);
         double globalAvg = 0.0;
-        for (int r = 0; r < d.n_proc; r++) globalAvg += sums[r] / cnt;      /* sum of local means, rank order */
+        for (int r = 0; r < d.n_proc; r++) globalAvg += (sums[2 * r] + sums[2 * r + 1]) / cnt;      /* sum of local means, rank order */
         globalAvg /= d.n_proc;
         if (s->mean_override) globalAvg = s->mean_value;
-        k_sub_scalar_padded<<<nbp, 256, 0, s->st>>>(L0.buf[SARASMG_RESIDUAL], L0.v, globalAvg);
-        TRY(kcheck(s, "k_sub_scalar_padded"));
+        k_sub_rows<<<nbp, 256, 0, s->st>>>(L0.buf[SARASMG_RESIDUAL], L0.v, globalAvg);
+        TRY(kcheck(s, "k_sub_rows"));
     }
 
     double prevResidual = 0.0;
