@@ -678,14 +678,14 @@ __device__ __forceinline__ double face_resolve(const double *A, const LevelView 
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(256) k_faces(double *A, const LevelView L, const FaceModes F) {
+__device__ __forceinline__ void faces_apply(double *A, const LevelView &L, const FaceModes &F, const long long tid, const long long nthr) {
     const int jlo = (DIM == 2) ? 0 : -1, nj = (DIM == 2) ? 1 : L.Fy;
     const int yE = L.ny - 1, zE = L.nz - 1, xE = L.nx - 1;
     const long long nZ = (F.m[4] | F.m[5]) ? (long long)L.Fx * nj : 0;                   /* (i, j) columns of the z faces */
     const long long nY = (DIM == 3 && (F.m[2] | F.m[3])) ? (long long)L.Fx * L.Fz : 0;   /* (i, k) of the y faces */
     const long long nX = (F.m[0] | F.m[1]) ? (long long)nj * L.Fz : 0;                   /* (j, k) of the x faces */
     const long long tot = nZ + nY + nX;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+    for (long long q = tid; q < tot; q += nthr) {
         if (q < nZ) {
             const int i = (int)(q / nj) - 1, j = jlo + (int)(q % nj);
             if (F.m[4] != FACE_NONE) A[mg_at(L, i, j, -1)] = face_resolve<DIM>(A, L, F, i, j, -1);
@@ -706,6 +706,10 @@ __global__ void __launch_bounds__(256) k_faces(double *A, const LevelView L, con
             if (F.m[1] != FACE_NONE) A[mg_at(L, xE + 1, j, k)] = face_resolve<DIM>(A, L, F, xE + 1, j, k);
         }
     }
+}
+template <int DIM>
+__global__ void __launch_bounds__(256) k_faces(double *A, const LevelView L, const FaceModes F) {
+    faces_apply<DIM>(A, L, F, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
 /* y-row pack/unpack for the inter-GPU halo (MPI_Type_vector of d3:492-497): row j of every x plane <-> contiguous buffer */
@@ -795,6 +799,162 @@ __global__ void __launch_bounds__(256) k_unpack_y2(double *__restrict__ A, const
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Peer-memory halo exchange over NVLink (one process per GPU, buffers shared with CUDA IPC).  The three  */
+/* kernels replace pack -> ncclSend/ncclRecv -> unpack of each phase with direct stores into the          */
+/* neighbour's receive buffers:                                                                           */
+/*   k_ipc_send_x   planes i = 1 / nx-2 -> left / right neighbour's x receive buffers, then their flags     */
+/*   k_ipc_x_to_y   wait for my x flags; receive buffers -> pads i = -1 / nx; rows j = 1 / ny-2 (with the    */
+/*                  fresh x pads taken from the receive buffers) -> front / back neighbour's y buffers, flags */
+/*   k_ipc_recv_y   wait for my y flags; receive buffers -> pads j = -1 / ny                                */
+/* Flags carry the exchange number (monotonic), receive buffers are double-buffered by its parity: a       */
+/* neighbour can only be one exchange ahead (it needs my flag of exchange e+1 to finish e+1), so it never    */
+/* overwrites a slot I have not consumed.  Data stores are made visible with __threadfence_system() before   */
+/* the last CTA of the grid raises the remote flags; consumers read the buffers with L1-bypassing loads.     */
+/* ------------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void ipc_wait_flag(const unsigned *flag, const unsigned epoch) {
+    if (!flag) return;
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    } while ((int)(v - epoch) < 0);
+}
+__device__ __forceinline__ void ipc_signal(unsigned *flag, const unsigned epoch) {
+    if (flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+/* every CTA calls this after its stores; the last one to arrive raises the flags */
+__device__ __forceinline__ void ipc_last_cta_signals(unsigned *counter, unsigned *flag_a, unsigned *flag_b, const unsigned epoch) {
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+        if (last) { *counter = 0u; __threadfence_system(); ipc_signal(flag_a, epoch); ipc_signal(flag_b, epoch); }
+    }
+}
+__device__ __forceinline__ double ld_cg_f64(const double *p) { return __ldcg(p); }
+
+__global__ void __launch_bounds__(256) k_ipc_send_x(const double *__restrict__ A, const LevelView L, const int planar,
+                                                    double *dst_left, double *dst_right, unsigned *flag_left, unsigned *flag_right,
+                                                    unsigned *counter, const unsigned epoch) {
+    const int nj = planar ? 1 : L.Fy;
+    const long long cnt = (long long)nj * L.Fz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
+        const int j = (planar ? 0 : -1) + (int)(q / L.Fz), k = (int)(q % L.Fz) - 1;
+        if (dst_left) dst_left[q] = A[mg_at(L, 1, j, k)];
+        if (dst_right) dst_right[q] = A[mg_at(L, L.nx - 2, j, k)];
+    }
+    ipc_last_cta_signals(counter, flag_left, flag_right, epoch);
+}
+
+__global__ void __launch_bounds__(256) k_ipc_x_to_y(double *__restrict__ A, const LevelView L, const int planar,
+                                                    const double *xr_lo, const double *xr_hi, const unsigned *wait_lo, const unsigned *wait_hi,
+                                                    double *dst_front, double *dst_back, unsigned *flag_front, unsigned *flag_back,
+                                                    unsigned *counter, const unsigned epoch) {
+    if (threadIdx.x == 0) { ipc_wait_flag(wait_lo, epoch); ipc_wait_flag(wait_hi, epoch); }
+    __syncthreads();
+    const int nj = planar ? 1 : L.Fy;
+    const long long cx = (xr_lo || xr_hi) ? (long long)nj * L.Fz : 0;
+    const long long cy = (dst_front || dst_back) ? (long long)L.Fx * L.Fz : 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cx + cy; q += (long long)gridDim.x * blockDim.x) {
+        if (q < cx) {
+            const int j = (planar ? 0 : -1) + (int)(q / L.Fz), k = (int)(q % L.Fz) - 1;
+            if (xr_lo) A[mg_at(L, -1, j, k)] = ld_cg_f64(xr_lo + q);
+            if (xr_hi) A[mg_at(L, L.nx, j, k)] = ld_cg_f64(xr_hi + q);
+        } else {
+            const long long w = q - cx;
+            const int i = (int)(w / L.Fz) - 1, k = (int)(w % L.Fz) - 1;
+            for (int side = 0; side < 2; side++) {
+                double *dst = side ? dst_back : dst_front;
+                if (!dst) continue;
+                const int j = side ? L.ny - 2 : 1;
+                double v;
+                if (i == -1 && xr_lo) v = ld_cg_f64(xr_lo + (long long)(j + 1) * L.Fz + (k + 1));
+                else if (i == L.nx && xr_hi) v = ld_cg_f64(xr_hi + (long long)(j + 1) * L.Fz + (k + 1));
+                else v = A[mg_at(L, i, j, k)];
+                dst[w] = v;
+            }
+        }
+    }
+    if (dst_front || dst_back) ipc_last_cta_signals(counter, flag_front, flag_back, epoch);
+}
+
+__global__ void __launch_bounds__(256) k_ipc_recv_y(double *__restrict__ A, const LevelView L, const double *yr_lo, const double *yr_hi,
+                                                    const unsigned *wait_lo, const unsigned *wait_hi, const unsigned epoch) {
+    if (threadIdx.x == 0) { ipc_wait_flag(wait_lo, epoch); ipc_wait_flag(wait_hi, epoch); }
+    __syncthreads();
+    const long long cnt = (long long)L.Fx * L.Fz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q / L.Fz) - 1, k = (int)(q % L.Fz) - 1;
+        if (yr_lo) A[mg_at(L, i, -1, k)] = ld_cg_f64(yr_lo + q);
+        if (yr_hi) A[mg_at(L, i, L.ny, k)] = ld_cg_f64(yr_hi + q);
+    }
+}
+
+/* Small levels: the whole updatePads (+ the wall BCs of imposeBC) in ONE single-CTA launch.  On the latency-bound coarse
+ * levels an exchange is a few thousand doubles, so the cost is launches and NVLink round trips, not bandwidth: the CTA
+ * sends its x faces, raises the flags, waits for its own, unpacks, sends the y rows (with the fresh x pads), waits,
+ * unpacks, and finishes with the face operations -- the same phases as the three kernels above, separated by
+ * __syncthreads instead of launches. */
+struct IpcPlan {
+    double *send[4];            /* neighbour's receive buffer for my left / right x plane and front / back y row (nullptr: none) */
+    unsigned *sflag[4];         /* the flag of that buffer, in the neighbour's arena */
+    const double *recv[4];      /* my receive buffers: x lo, x hi, y lo, y hi */
+    const unsigned *rflag[4];   /* my flags */
+};
+template <int DIM>
+__global__ void __launch_bounds__(1024) k_ipc_exchange_cta(double *A, const LevelView L, const IpcPlan P, const unsigned epoch,
+                                                          const FaceModes self_x, const FaceModes self_y, const FaceModes bc) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const bool planar = (DIM == 2);
+    const int nj = planar ? 1 : L.Fy;
+    const int cx = nj * L.Fz, cy = planar ? 0 : L.Fx * L.Fz;
+    faces_apply<DIM>(A, L, self_x, tid, nthr);                     /* periodic self-neighbour in x (no-op when all modes are NONE) */
+    if (P.send[0] || P.send[1]) {
+        for (int q = tid; q < cx; q += nthr) {
+            const int j = (planar ? 0 : -1) + q / L.Fz, k = q % L.Fz - 1;
+            if (P.send[0]) P.send[0][q] = A[mg_at(L, 1, j, k)];
+            if (P.send[1]) P.send[1][q] = A[mg_at(L, L.nx - 2, j, k)];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) { ipc_signal(P.sflag[0], epoch); ipc_signal(P.sflag[1], epoch); }
+    }
+    if (tid == 0) { ipc_wait_flag(P.rflag[0], epoch); ipc_wait_flag(P.rflag[1], epoch); }
+    __syncthreads();
+    if (P.recv[0] || P.recv[1])
+        for (int q = tid; q < cx; q += nthr) {
+            const int j = (planar ? 0 : -1) + q / L.Fz, k = q % L.Fz - 1;
+            if (P.recv[0]) A[mg_at(L, -1, j, k)] = ld_cg_f64(P.recv[0] + q);
+            if (P.recv[1]) A[mg_at(L, L.nx, j, k)] = ld_cg_f64(P.recv[1] + q);
+        }
+    __syncthreads();
+    if (DIM == 3) {
+        faces_apply<DIM>(A, L, self_y, tid, nthr);
+        if (P.send[2] || P.send[3]) {
+            for (int q = tid; q < cy; q += nthr) {
+                const int i = q / L.Fz - 1, k = q % L.Fz - 1;
+                if (P.send[2]) P.send[2][q] = A[mg_at(L, i, 1, k)];
+                if (P.send[3]) P.send[3][q] = A[mg_at(L, i, L.ny - 2, k)];
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) { ipc_signal(P.sflag[2], epoch); ipc_signal(P.sflag[3], epoch); }
+        }
+        if (tid == 0) { ipc_wait_flag(P.rflag[2], epoch); ipc_wait_flag(P.rflag[3], epoch); }
+        __syncthreads();
+        if (P.recv[2] || P.recv[3])
+            for (int q = tid; q < cy; q += nthr) {
+                const int i = q / L.Fz - 1, k = q % L.Fz - 1;
+                if (P.recv[2]) A[mg_at(L, i, -1, k)] = ld_cg_f64(P.recv[2] + q);
+                if (P.recv[3]) A[mg_at(L, i, L.ny, k)] = ld_cg_f64(P.recv[3] + q);
+            }
+        __syncthreads();
+    }
+    faces_apply<DIM>(A, L, bc, tid, nthr);                          /* wall BCs of imposeBC (all NONE for a bare updatePads) */
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* full-weighting restriction (d3:270-297, d2:222-235): thread per coarse point, sums in source order */
 /* ------------------------------------------------------------------------------------------------ */
 template <int DIM>
@@ -834,6 +994,46 @@ __global__ void __launch_bounds__(256) k_coarsen(const double *__restrict__ T, c
         Rc[mg_at(Lc, i, 0, k)] = facePoints + vertPoints + TF(i2, 0, k2) * 0.25;
     }
 #undef TF
+}
+
+/* The 3-D restriction as an x-marching kernel: a thread owns the coarse column (J, K) and walks I.  The nine fine values
+ * of plane 2I+1 it loaded for coarse point I are the plane 2(I+1)-1 values of the next point, so every step loads two
+ * new fine planes (3 rows each: one aligned 128-bit load for (k2, k2+1) plus one 64-bit load for k2-1) instead of 27
+ * scalars, and all of a step's loads are issued before the sums.  Sums in the order of d3:270-297. */
+__global__ void __launch_bounds__(256) k_coarsen_march(const double *__restrict__ T, const LevelView Lf, double *__restrict__ Rc,
+                                                       const LevelView Lc, const int ichunk) {
+    const int K = blockIdx.x * blockDim.x + threadIdx.x;
+    const int J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (K >= Lc.nz || J >= Lc.ny) return;
+    const int I0 = blockIdx.z * ichunk, I1 = min(I0 + ichunk, Lc.nx);
+    const long long fplane = Lf.plane;
+    const int fp = Lf.pitch;
+    /* fine row j2 = 2J, column k2 = 2K of x-plane index 0 (i = -1) */
+    const double *t = T + (long long)(2 * J + 1) * fp + (2 * K + 1 + MG_LEAD);
+    double *rc = Rc + (long long)(J + 1) * Lc.pitch + (K + 1 + MG_LEAD);
+    double A[3][3], B[3][3], C[3][3];
+#define LOAD_PLANE(M, base)                                                          \
+    {                                                                                \
+        _Pragma("unroll") for (int r = 0; r < 3; r++) {                              \
+            const double *row = (base) + (long long)(r - 1) * fp;                    \
+            const double2 v = ld2(row);                                              \
+            M[r][0] = row[-1]; M[r][1] = v.x; M[r][2] = v.y;                         \
+        }                                                                            \
+    }
+    LOAD_PLANE(A, t + (long long)(2 * I0) * fplane);                /* fine plane 2*I0 - 1 */
+    for (int I = I0; I < I1; ++I) {
+        const double *b = t + (long long)(2 * I + 1) * fplane;      /* fine plane 2I */
+        LOAD_PLANE(B, b);
+        LOAD_PLANE(C, b + fplane);
+        const double facePoints = (C[1][1] + A[1][1] + B[2][1] + B[0][1] + B[1][2] + B[1][0]) * 0.0625;
+        const double edgePoints = (C[2][1] + C[0][1] + A[0][1] + A[2][1] + B[2][2] + B[0][2] + B[0][0] + B[2][0] +
+                                   C[1][2] + C[1][0] + A[1][0] + A[1][2]) * 0.03125;
+        const double vertPoints = (C[2][2] + C[2][0] + C[0][2] + A[2][2] + C[0][0] + A[2][0] + A[0][2] + A[0][0]) * 0.015625;
+        rc[(long long)(I + 1) * Lc.plane] = facePoints + edgePoints + vertPoints + B[1][1] * 0.125;
+#pragma unroll
+        for (int r = 0; r < 3; r++) { A[r][0] = C[r][0]; A[r][1] = C[r][1]; A[r][2] = C[r][2]; }
+    }
+#undef LOAD_PLANE
 }
 
 /* ------------------------------------------------------------------------------------------------ */

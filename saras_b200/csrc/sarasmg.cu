@@ -97,6 +97,15 @@ struct sarasmg_solver_s {
     bool has_comm;
     double *xs[2], *xr[2], *ys[2], *yr[2];
     double *d_gather;           /* n_proc * 4 doubles */
+    /* peer-memory halo exchange (CUDA IPC over NVLink): receive arena of this rank and the mapped arenas of its face neighbours */
+    bool ipc_ok;
+    double *ipc_arena;
+    size_t ipc_slot, ipc_xc, ipc_yc;        /* doubles per parity slot; level-0 x / y face counts (fix the layout of a slot) */
+    double *ipc_peer[4];                    /* mapped arena of the left / right / front / back neighbour (nullptr: none) */
+    void *ipc_opened[4];
+    int ipc_nopened;
+    unsigned ipc_epoch;
+    long long ipc_cta_max;                  /* faces up to this many doubles are exchanged by the single-CTA kernel */
     /* agglomerated coarsest-level solve (k_coarse_solve_blocks): all ranks' coarsest arrays, block table, metric copies */
     double *agg_P, *agg_R;      /* n_proc * lev[D].elems doubles each */
     CoarseBlock *agg_tab;
@@ -117,6 +126,7 @@ struct sarasmg_solver_s {
     int mean_override;          /* test hook: use mean_value instead of the device-computed RHS mean */
     double mean_value;
     int prof_max_level;         /* events only for operators on levels <= this */
+    bool coarsen_legacy;        /* SARASMG_COARSEN_LEGACY: thread-per-coarse-point restriction kernel */
     bool prolong_legacy;        /* SARASMG_PROLONG_LEGACY: thread-per-fine-point prolongation kernel */
     bool no_pow2;               /* SARASMG_NO_POW2: keep the general exact-division path even when the divisors are powers of two (tests) */
     bool gs_legacy;             /* SARASMG_GS_LEGACY: one launch per hyperplane instead of the skewed single-launch sweep */
@@ -256,7 +266,9 @@ static PadPlan pad_plan(const S *s) {
 /* Neighbour == own rank (periodic, one rank along that axis): local copies (k_faces).                 */
 /* Neighbour == other rank: pack -> grouped ncclSend/ncclRecv -> unpack on the solver stream.          */
 /* ------------------------------------------------------------------------------------------------ */
-static int update_pads(S *s, int level, double *A) {
+/* bc != nullptr: the caller is imposeBC and wants these wall modes applied after the exchange; *bc_done tells it whether
+ * the exchange kernel already did (single-CTA path on small levels) */
+static int update_pads(S *s, int level, double *A, const int *bc = nullptr, bool *bc_done = nullptr) {
     const Level &L = s->lev[level];
     const LevelView &v = L.v;
     const int *fr = s->d.face_ranks;
@@ -267,6 +279,66 @@ static int update_pads(S *s, int level, double *A) {
 
     const int nj = s->planar ? 1 : v.Fy;
     const long long cx = (long long)nj * v.Fz, cy = (long long)v.Fx * v.Fz;
+    if (s->ipc_ok) {
+        /* peer-memory path: three launches, no library call (kernels and protocol in mg_kernels.cuh) */
+        const unsigned ep = ++s->ipc_epoch;
+        const int slot = (int)(ep & 1u);
+        const size_t xc = s->ipc_xc, yc = s->ipc_yc, sb = (size_t)slot * s->ipc_slot;
+        unsigned *myflags = (unsigned *)(s->ipc_arena + 2 * s->ipc_slot);
+        auto peer_buf = [&](int f, size_t off) { return s->ipc_peer[f] + sb + off; };
+        auto peer_flag = [&](int f, int side) { return (unsigned *)(s->ipc_peer[f] + 2 * s->ipc_slot) + side * 2 + slot; };
+        double *my = s->ipc_arena + sb;
+        const bool xrem = pp.rl || pp.rr, yrem = pp.rf || pp.rb;
+        if (std::max(cx, s->planar ? 0LL : cy) <= s->ipc_cta_max) {
+            /* small level: the whole exchange, and the wall BCs of imposeBC, in one single-CTA launch */
+            IpcPlan P;
+            const bool rem[4] = {pp.rl, pp.rr, pp.rf, pp.rb};
+            const size_t send_off[4] = {xc, 0, 2 * xc + yc, 2 * xc}, recv_off[4] = {0, xc, 2 * xc, 2 * xc + yc};
+            const int send_side[4] = {1, 0, 3, 2};
+            for (int f = 0; f < 4; f++) {
+                P.send[f] = rem[f] ? peer_buf(f, send_off[f]) : nullptr;
+                P.sflag[f] = rem[f] ? peer_flag(f, send_side[f]) : nullptr;
+                P.recv[f] = rem[f] ? my + recv_off[f] : nullptr;
+                P.rflag[f] = rem[f] ? myflags + f * 2 + slot : nullptr;
+            }
+            FaceModes fx, fy, fb;
+            for (int q = 0; q < 6; q++) { fx.m[q] = FACE_NONE; fy.m[q] = FACE_NONE; fb.m[q] = bc ? bc[q] : FACE_NONE; }
+            fx.m[0] = pp.self[0]; fx.m[1] = pp.self[1]; fy.m[2] = pp.self[2]; fy.m[3] = pp.self[3];
+            if (s->planar) { fb.m[2] = FACE_NONE; fb.m[3] = FACE_NONE; }
+            fx.xwall = fx.ywall = fx.zwall = fy.xwall = fy.ywall = fy.zwall = nullptr;
+            fb.xwall = s->d_wall[0]; fb.ywall = s->d_wall[1]; fb.zwall = s->d_wall[2];
+            if (s->planar) k_ipc_exchange_cta<2><<<1, 1024, 0, s->st>>>(A, v, P, ep, fx, fy, fb);
+            else k_ipc_exchange_cta<3><<<1, 1024, 0, s->st>>>(A, v, P, ep, fx, fy, fb);
+            TRY(kcheck(s, "k_ipc_exchange_cta"));
+            if (bc_done) *bc_done = true;
+            return 0;
+        }
+        if (pp.self[0] | pp.self[1]) {
+            const int m[6] = {pp.self[0], pp.self[1], FACE_NONE, FACE_NONE, FACE_NONE, FACE_NONE};
+            TRY(launch_faces(s, A, L, m, false));
+        }
+        if (xrem) {
+            k_ipc_send_x<<<std::min(face_blocks(cx), 296u), 256, 0, s->st>>>(A, v, s->planar,
+                pp.rl ? peer_buf(0, xc) : nullptr, pp.rr ? peer_buf(1, 0) : nullptr,
+                pp.rl ? peer_flag(0, 1) : nullptr, pp.rr ? peer_flag(1, 0) : nullptr, myflags + 16, ep);
+            TRY(kcheck(s, "k_ipc_send_x"));
+        }
+        k_ipc_x_to_y<<<std::min(face_blocks(cx + cy), 296u), 256, 0, s->st>>>(A, v, s->planar,
+            pp.rl ? my : nullptr, pp.rr ? my + xc : nullptr, pp.rl ? myflags + 0 * 2 + slot : nullptr, pp.rr ? myflags + 1 * 2 + slot : nullptr,
+            pp.rf ? peer_buf(2, 2 * xc + yc) : nullptr, pp.rb ? peer_buf(3, 2 * xc) : nullptr,
+            pp.rf ? peer_flag(2, 3) : nullptr, pp.rb ? peer_flag(3, 2) : nullptr, myflags + 17, ep);
+        TRY(kcheck(s, "k_ipc_x_to_y"));
+        if (pp.self[2] | pp.self[3]) {
+            const int m[6] = {FACE_NONE, FACE_NONE, pp.self[2], pp.self[3], FACE_NONE, FACE_NONE};
+            TRY(launch_faces(s, A, L, m, false));
+        }
+        if (yrem) {
+            k_ipc_recv_y<<<std::min(face_blocks(cy), 296u), 256, 0, s->st>>>(A, v, pp.rf ? my + 2 * xc : nullptr, pp.rb ? my + 2 * xc + yc : nullptr,
+                pp.rf ? myflags + 2 * 2 + slot : nullptr, pp.rb ? myflags + 3 * 2 + slot : nullptr, ep);
+            TRY(kcheck(s, "k_ipc_recv_y"));
+        }
+        return 0;
+    }
     /* ---- x phase ---- */
     if (pp.self[0] | pp.self[1]) {
         const int m[6] = {pp.self[0], pp.self[1], FACE_NONE, FACE_NONE, FACE_NONE, FACE_NONE};
@@ -344,7 +416,9 @@ static int impose_bc(S *s, int level) {
         for (int q = 0; q < 6; q++) all[q] = (m[q] != FACE_NONE) ? m[q] : pp.self[q];     /* a wall BC is applied after, and over, the pad copy */
         return launch_faces(s, P, L, all, false);
     }
-    TRY(update_pads(s, level, P));
+    bool bc_done = false;
+    TRY(update_pads(s, level, P, m, &bc_done));
+    if (bc_done) return 0;
     ProfScope ps(s, SARASMG_K_BC, level);
     return launch_faces(s, P, L, m, true);
 }
@@ -589,10 +663,17 @@ static int op_coarsen(S *s) {
     ProfScope ps(s, SARASMG_K_COARSEN, pLevel);
     if (s->planar) {
         k_coarsen<2><<<dim3(cdiv(Lc.v.nz, 128), 1, Lc.v.nx), dim3(128, 1, 1), 0, s->st>>>(Lf.buf[SARASMG_TMP], Lf.v, Lc.buf[SARASMG_RESIDUAL], Lc.v);
-    } else {
+    } else if (s->coarsen_legacy) {
         int bx = 64, by = 4;
         while (bx > 4 && bx / 2 >= Lc.v.nz) { bx /= 2; by *= 2; }
         k_coarsen<3><<<dim3(cdiv(Lc.v.nz, bx), cdiv(Lc.v.ny, by), Lc.v.nx), dim3(bx, by, 1), 0, s->st>>>(Lf.buf[SARASMG_TMP], Lf.v, Lc.buf[SARASMG_RESIDUAL], Lc.v);
+    } else {
+        int bx = 32, by = 8;
+        while (bx > 4 && bx / 2 >= Lc.v.nz) { bx /= 2; by *= 2; }
+        const unsigned gx = cdiv(Lc.v.nz, bx), gy = cdiv(Lc.v.ny, by);
+        int ichunk = 32;
+        while (ichunk > 2 && (long long)gx * gy * cdiv(Lc.v.nx, ichunk) < 148LL * 8) ichunk /= 2;
+        k_coarsen_march<<<dim3(gx, gy, cdiv(Lc.v.nx, ichunk)), dim3(bx, by, 1), 0, s->st>>>(Lf.buf[SARASMG_TMP], Lf.v, Lc.buf[SARASMG_RESIDUAL], Lc.v, ichunk);
     }
     return kcheck(s, "k_coarsen");
 }
@@ -721,6 +802,69 @@ static void bc_plan(const S *s, BcPlan &B) {
     B.bc_x_lo = m[0]; B.bc_x_hi = m[1]; B.bc_y_lo = m[2]; B.bc_y_hi = m[3]; B.bc_z_lo = m[4]; B.bc_z_hi = m[5];
     B.xwall = s->d_wall[0]; B.ywall = s->d_wall[1]; B.zwall = s->d_wall[2];
     B.planar = s->planar;
+}
+
+/* Peer-memory halos: every rank allocates a receive arena (two parity slots of x / y face buffers + flags), the CUDA IPC
+ * handles travel through one ncclAllGather, and each rank maps the arenas of its face neighbours.  All ranks agree (MIN
+ * all-reduce) on whether the mapping worked; otherwise, or with SARASMG_HALO=nccl, the grouped ncclSend/ncclRecv path stays. */
+static int setup_ipc_halo(S *s) {
+    const sarasmg_desc &d = s->d;
+    const int np = d.n_proc;
+    const LevelView &v0 = s->lev[0].v;
+    const char *mode = getenv("SARASMG_HALO");
+    const bool want = !(mode && strcmp(mode, "nccl") == 0);
+    s->ipc_xc = (size_t)(s->planar ? 1 : v0.Fy) * v0.Fz;
+    s->ipc_yc = s->planar ? 0 : (size_t)v0.Fx * v0.Fz;
+    s->ipc_slot = 2 * s->ipc_xc + 2 * s->ipc_yc;
+    const size_t arena_bytes = (2 * s->ipc_slot + 64) * sizeof(double);
+    int ok = want ? 1 : 0;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok) {
+        if (cudaMalloc(&s->ipc_arena, arena_bytes) != cudaSuccess) { cudaGetLastError(); s->ipc_arena = nullptr; ok = 0; }
+        else {
+            CU(cudaMemsetAsync(s->ipc_arena, 0, arena_bytes, s->st));
+            if (cudaIpcGetMemHandle(&mine, s->ipc_arena) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        }
+    }
+    /* all-gather {handle, ok} */
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    std::vector<unsigned char> hmine(rec, 0), hall(rec * np, 0);
+    memcpy(hmine.data(), &mine, sizeof(mine));
+    hmine[sizeof(mine)] = (unsigned char)ok;
+    unsigned char *dm = nullptr, *da = nullptr;
+    CU(cudaMalloc(&dm, rec));
+    CU(cudaMalloc(&da, rec * np));
+    CU(cudaMemcpyAsync(dm, hmine.data(), rec, cudaMemcpyHostToDevice, s->st));
+    NC(ncclAllGather(dm, da, rec, ncclUint8, s->comm, s->st));
+    CU(cudaMemcpyAsync(hall.data(), da, rec * np, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    for (int r = 0; r < np; r++) ok = ok && hall[r * rec + sizeof(mine)];
+    if (ok) {
+        for (int f = 0; f < 4; f++) {
+            const int r = d.face_ranks[f];
+            if (r == SARASMG_PROC_NULL || r == d.rank || (s->planar && f >= 2)) continue;
+            for (int g = 0; g < f; g++) if (d.face_ranks[g] == r && s->ipc_peer[g]) s->ipc_peer[f] = s->ipc_peer[g];   /* same peer on two sides */
+            if (s->ipc_peer[f]) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, hall.data() + r * rec, sizeof(h));
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            s->ipc_opened[s->ipc_nopened++] = ptr;
+            s->ipc_peer[f] = (double *)ptr;
+        }
+    }
+    /* agree: MIN over ranks of the final status (reuses the small device buffers) */
+    int *di = (int *)dm;
+    CU(cudaMemcpyAsync(di, &ok, sizeof(int), cudaMemcpyHostToDevice, s->st));
+    NC(ncclAllReduce(di, di, 1, ncclInt, ncclMin, s->comm, s->st));
+    CU(cudaMemcpyAsync(&ok, di, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaFree(dm)); CU(cudaFree(da));
+    s->ipc_ok = (ok != 0);
+    if (!s->ipc_ok && want && d.rank == 0 && getenv("SARASMG_VERBOSE"))
+        fprintf(stderr, "saras-mg: CUDA IPC halo buffers unavailable, using ncclSend/ncclRecv\n");
+    return 0;
 }
 
 /* One-time exchange for the agglomerated coarsest solve: every rank learns every rank's face neighbours, wall flags and
@@ -1054,12 +1198,16 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     s->gs_legacy = getenv("SARASMG_GS_LEGACY") != nullptr;
     s->no_pow2 = getenv("SARASMG_NO_POW2") != nullptr;
     s->prolong_legacy = getenv("SARASMG_PROLONG_LEGACY") != nullptr;
+    s->coarsen_legacy = getenv("SARASMG_COARSEN_LEGACY") != nullptr;
     for (int q = 0; q < 8; q++) s->user_ev[q] = nullptr;
     memset(s->prof_ms, 0, sizeof(s->prof_ms));
     memset(s->prof_n, 0, sizeof(s->prof_n));
     for (int q = 0; q < 3; q++) s->d_wall[q] = nullptr;
     for (int q = 0; q < 2; q++) s->xs[q] = s->xr[q] = s->ys[q] = s->yr[q] = nullptr;
     s->d_gather = nullptr;
+    s->ipc_cta_max = getenv("SARASMG_IPC_CTA_MAX") ? atoll(getenv("SARASMG_IPC_CTA_MAX")) : 16384;
+    s->ipc_ok = false; s->ipc_arena = nullptr; s->ipc_nopened = 0; s->ipc_epoch = 0;
+    for (int q = 0; q < 4; q++) { s->ipc_peer[q] = nullptr; s->ipc_opened[q] = nullptr; }
     s->agg_P = s->agg_R = nullptr; s->agg_tab = nullptr; s->agg_met = nullptr; s->agg_ok = false;
     s->coarse_legacy = getenv("SARASMG_COARSE_LEGACY") != nullptr;
     CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
@@ -1169,6 +1317,7 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
         }
         CU(cudaMalloc(&s->d_gather, (size_t)desc->n_proc * 8 * sizeof(double)));
         TRY(setup_agglomeration(s));
+        TRY(setup_ipc_halo(s));
     }
     if (desc->n_proc == 1) TRY(setup_agglomeration(s));
     s->d.nccl_id = nullptr;     /* the caller's buffers are not retained */
@@ -1193,6 +1342,8 @@ int sarasmg_destroy(sarasmg_handle s) {
     for (int q = 0; q < 3; q++) if (s->d_wall[q]) cudaFree(s->d_wall[q]);
     for (int q = 0; q < 2; q++) { cudaFree(s->xs[q]); cudaFree(s->xr[q]); cudaFree(s->ys[q]); cudaFree(s->yr[q]); }
     cudaFree(s->d_gather);
+    for (int q = 0; q < s->ipc_nopened; q++) cudaIpcCloseMemHandle(s->ipc_opened[q]);
+    cudaFree(s->ipc_arena);
     cudaFree(s->agg_P); cudaFree(s->agg_R); cudaFree(s->agg_tab); cudaFree(s->agg_met);
     cudaFree(s->d_part); cudaFree(s->d_scal); cudaFree(s->d_iters);
     cudaFreeHost(s->h_scal); cudaFreeHost(s->h_iters);

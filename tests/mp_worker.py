@@ -108,12 +108,21 @@ def run_gpu(rank, world, local):
 
     cases = gpu_cases(world)
     # the first case once more with the host-driven coarsest solve (one halo exchange + all-gather per iteration)
-    cases.append(dict(cases[0], name=cases[0]["name"] + "_coarse_legacy", _env="SARASMG_COARSE_LEGACY"))
+    cases.append(dict(cases[0], name=cases[0]["name"] + "_coarse_legacy", _env="SARASMG_COARSE_LEGACY=1"))
+    # the default halo path is peer memory over CUDA IPC; run two cases with the grouped ncclSend/ncclRecv path as well
+    cases.append(dict(cases[0], name=cases[0]["name"] + "_halo_nccl", _env="SARASMG_HALO=nccl"))
+    cases.append(dict(cases[1], name=cases[1]["name"] + "_halo_nccl", _env="SARASMG_HALO=nccl"))
+    # small levels use the single-CTA peer-memory exchange; force the three-kernel version (large levels) onto these grids too
+    cases.append(dict(cases[0], name=cases[0]["name"] + "_ipc_3kernel", _env="SARASMG_IPC_CTA_MAX=0"))
+    cases.append(dict(cases[1], name=cases[1]["name"] + "_ipc_3kernel", _env="SARASMG_IPC_CTA_MAX=0"))
+    cases.append(dict(cases[3], name=cases[3]["name"] + "_ipc_3kernel", _env="SARASMG_IPC_CTA_MAX=0"))
     for case in cases:
         base = {k: v for k, v in case.items() if k not in ("name", "_env")}
-        os.environ.pop("SARASMG_COARSE_LEGACY", None)
+        for key in ("SARASMG_COARSE_LEGACY", "SARASMG_HALO", "SARASMG_IPC_CTA_MAX"):
+            os.environ.pop(key, None)
         if case.get("_env"):
-            os.environ[case["_env"]] = "1"
+            key, val = case["_env"].split("=")
+            os.environ[key] = val
         for gs in (0, 1):
             cfg = dict(base, gsSmooth=gs, vcCount=6, resType=2, mgTolerance=1e-7)
             o = Oracle(**cfg)

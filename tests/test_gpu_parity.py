@@ -75,6 +75,7 @@ def _select_path(monkeypatch, path):
     if path == "general":
         monkeypatch.setenv("SARASMG_NO_POW2", "1")
         monkeypatch.setenv("SARASMG_PROLONG_LEGACY", "1")
+        monkeypatch.setenv("SARASMG_COARSEN_LEGACY", "1")
     if path in ("tma", "tma_general"):
         # the TMA-staged marching kernels normally serve levels with nz >= 257; force them onto these small grids, where
         # almost every tile hangs over the array edge (zero-filled by the hardware, masked in the kernel)
