@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--tolerance", type=float, default=1.0e-6, help="parser::mgTolerance (reference YAML default 1e-6): coarsest-level solve and stagnation test")
     ap.add_argument("--breakdown", action="store_true", help="one extra solve with every level profiled; per-(operator, level) table on stderr")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ttt", action="store_true", help="skip the time-to-tolerance solve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-index", type=int, default=8, help="grid index of the bounded CPU sample (8 -> 257^3)")
     return ap.parse_args()
@@ -339,6 +340,39 @@ def run_b200(a):
             print("breakdown total %.3f ms in events, last_solve_ms %.3f" % (tot, s.last_solve_ms()), file=sys.stderr)
         s.set_profile_max_level(1)
 
+    # per-(operator, level) achieved bandwidth of EVERY level: one extra solve outside the timed region with all levels bracketed
+    s.set_profile_max_level(1 << 20)
+    s.reset_counters()
+    s.solve_resident()
+    per_level_all = []
+    for lvl in range(depth + 1):
+        for kind, name in ((capi.K_SMOOTH, "smooth"), (capi.K_RESIDUAL, "residual"), (capi.K_COARSEN, "coarsen"),
+                           (capi.K_PROLONG, "prolong"), (capi.K_ERROR, "error"), (capi.K_HALO, "halo"), (capi.K_BC, "bc"),
+                           (capi.K_COARSE_SOLVE, "coarse_solve")):
+            ms, n = s.profile_query(kind, lvl)
+            if n == 0:
+                continue
+            e = dict(level=lvl, op=name, launches=int(n), avg_us=1e3 * ms / n)
+            if name in BYTES_PER_LUP:
+                gbs = BYTES_PER_LUP[name] * level_points_local[lvl] / (ms / n * 1e-3) / 1e9
+                e.update(gbs=gbs, frac=gbs / peak)
+            per_level_all.append(e)
+    s.set_profile_max_level(1)
+
+    # time to tolerance: the same hierarchy run until the reference's stagnation test |r_prev - r| < mgTolerance stops it
+    ttt = None
+    if not a.no_ttt:
+        s.set_vc_count(60)
+        s.reset_counters()
+        barrier(); s.synchronize()
+        s.event_record(2)
+        out_t = s.solve_resident()
+        s.event_record(3)
+        ms_t = allmax(s.event_elapsed_ms(2, 3))
+        ttt = dict(ms=ms_t, cycles=int(out_t["cycles"]), tolerance=a.tolerance, final_residual=float(out_t["residuals"][-1]),
+                   rule="poisson.cc:145 stagnation test, at most 60 cycles")
+        s.set_vc_count(a.cycles)
+
     # ---- end-to-end arm: mgSolver.mgSolve(Pp, mgRHS) on host plainsf arrays ---------------------------------------
     e2e = None
     if not a.no_e2e:
@@ -375,7 +409,8 @@ def run_b200(a):
                                 cycles_per_step=int(outs[-1]["cycles"]), final_residual=float(outs[-1]["residuals"][-1]),
                                 coarse_iters=[int(v) for v in outs[-1]["coarse_iters"]], lups_per_step=lups_step,
                                 fine_point_vcycles_per_s=level_points[0] * outs[-1]["cycles"] * a.steps / (ms_total * 1e-3)),
-                    clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, per_level=per_level, cpu_baseline=cpu, breakdown=breakdown)
+                    clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, per_level=per_level, per_level_all=per_level_all,
+                    time_to_tolerance=ttt, cpu_baseline=cpu, breakdown=breakdown)
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:

@@ -159,6 +159,9 @@ int sarasmg_host_register(sarasmg_handle h, const void *ptr, unsigned long long 
  * Neumann/periodic solve amplifies it ~100x.  With enable != 0 the solver subtracts `value` instead, so a test can feed
  * the oracle's mean and then require bit-exact fields in production mode as well. */
 int sarasmg_debug_set_rhs_mean(sarasmg_handle h, int enable, double value);
+/* parser::vcCount of the handle (the reference reads it once from the YAML; a benchmark uses this to run the same hierarchy
+ * to stagnation for the time-to-tolerance figure).  History buffers passed to the solve calls must hold `count` entries. */
+int sarasmg_set_vc_count(sarasmg_handle h, int count);
 /* blocks until all work of the handle has finished */
 int sarasmg_synchronize(sarasmg_handle h);
 

@@ -51,6 +51,7 @@ SYMBOLS = [
     "sarasmg_timers", "sarasmg_kernel_launches", "sarasmg_reset_counters", "sarasmg_profile_query",
     "sarasmg_last_solve_ms", "sarasmg_synchronize", "sarasmg_debug_set_rhs_mean",
     "sarasmg_set_profile_max_level", "sarasmg_event_record", "sarasmg_event_elapsed_ms", "sarasmg_host_register",
+    "sarasmg_set_vc_count",
 ]
 
 
@@ -100,6 +101,7 @@ def load():
     lib.sarasmg_event_record.argtypes = [vp, C.c_int]
     lib.sarasmg_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, _dp]
     lib.sarasmg_host_register.argtypes = [vp, C.c_void_p, C.c_ulonglong]
+    lib.sarasmg_set_vc_count.argtypes = [vp, C.c_int]
     _lib = lib
     return lib
 
@@ -331,6 +333,10 @@ class Solver:
 
     def debug_set_rhs_mean(self, enable, value=0.0):
         self._check(self.lib.sarasmg_debug_set_rhs_mean(self.h, int(enable), float(value)))
+
+    def set_vc_count(self, count):
+        self._check(self.lib.sarasmg_set_vc_count(self.h, int(count)))
+        self.vc_count = max(int(count), 1)
 
     def synchronize(self):
         self._check(self.lib.sarasmg_synchronize(self.h))

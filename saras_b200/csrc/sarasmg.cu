@@ -1205,7 +1205,7 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     for (int q = 0; q < 3; q++) s->d_wall[q] = nullptr;
     for (int q = 0; q < 2; q++) s->xs[q] = s->xr[q] = s->ys[q] = s->yr[q] = nullptr;
     s->d_gather = nullptr;
-    s->ipc_cta_max = getenv("SARASMG_IPC_CTA_MAX") ? atoll(getenv("SARASMG_IPC_CTA_MAX")) : 16384;
+    s->ipc_cta_max = getenv("SARASMG_IPC_CTA_MAX") ? atoll(getenv("SARASMG_IPC_CTA_MAX")) : 4096;
     s->ipc_ok = false; s->ipc_arena = nullptr; s->ipc_nopened = 0; s->ipc_epoch = 0;
     for (int q = 0; q < 4; q++) { s->ipc_peer[q] = nullptr; s->ipc_opened[q] = nullptr; }
     s->agg_P = s->agg_R = nullptr; s->agg_tab = nullptr; s->agg_met = nullptr; s->agg_ok = false;
@@ -1684,6 +1684,11 @@ int sarasmg_debug_set_rhs_mean(sarasmg_handle s, int enable, double value) {
     if (!s) return set_err("null handle");
     s->mean_override = enable ? 1 : 0;
     s->mean_value = value;
+    return 0;
+}
+int sarasmg_set_vc_count(sarasmg_handle s, int count) {
+    if (!s || count < 0) return set_err("sarasmg_set_vc_count: bad argument");
+    s->d.vc_count = count;
     return 0;
 }
 int sarasmg_synchronize(sarasmg_handle s) { ENTER(s); CU(cudaStreamSynchronize(s->st)); return 0; }
