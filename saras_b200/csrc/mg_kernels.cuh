@@ -834,9 +834,27 @@ __device__ __forceinline__ void ipc_last_cta_signals(unsigned *counter, unsigned
 }
 __device__ __forceinline__ double ld_cg_f64(const double *p) { return __ldcg(p); }
 
-__global__ void __launch_bounds__(256) k_ipc_send_x(const double *__restrict__ A, const LevelView L, const int planar,
-                                                    double *dst_left, double *dst_right, unsigned *flag_left, unsigned *flag_right,
-                                                    unsigned *counter, const unsigned epoch) {
+/* Addresses of one exchange.  Pointers are those of parity slot 0; slot 1 lies `slot_stride` doubles (buffers) / one
+ * entry (flags) further.  The exchange number is *base + add: `base` is a device word the host (re)sets before a CUDA graph
+ * of a whole V-cycle is replayed, `add` the position of the exchange inside the graph (or since the last reset), so the
+ * same captured kernels carry fresh, dense exchange numbers on every replay. */
+struct IpcPlan {
+    double *send[4];            /* neighbour's receive buffer for my left / right x plane and front / back y row (nullptr: none) */
+    unsigned *sflag[4];         /* the flag of that buffer, in the neighbour's arena */
+    const double *recv[4];      /* my receive buffers: x lo, x hi, y lo, y hi */
+    const unsigned *rflag[4];   /* my flags */
+    long long slot_stride;
+    const unsigned *base;
+    unsigned add;
+    unsigned *counter;          /* two arrival counters (x phase, y phase) of the multi-CTA kernels */
+};
+__device__ __forceinline__ unsigned ipc_epoch(const IpcPlan &P) { return *P.base + P.add; }
+template <typename T>
+__device__ __forceinline__ T *ipc_slot(T *p, const unsigned ep, const long long stride) { return p ? p + (ep & 1u) * stride : p; }
+
+__global__ void __launch_bounds__(256) k_ipc_send_x(const double *__restrict__ A, const LevelView L, const int planar, const IpcPlan P) {
+    const unsigned ep = ipc_epoch(P);
+    double *dst_left = ipc_slot(P.send[0], ep, P.slot_stride), *dst_right = ipc_slot(P.send[1], ep, P.slot_stride);
     const int nj = planar ? 1 : L.Fy;
     const long long cnt = (long long)nj * L.Fz;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
@@ -844,15 +862,15 @@ __global__ void __launch_bounds__(256) k_ipc_send_x(const double *__restrict__ A
         if (dst_left) dst_left[q] = A[mg_at(L, 1, j, k)];
         if (dst_right) dst_right[q] = A[mg_at(L, L.nx - 2, j, k)];
     }
-    ipc_last_cta_signals(counter, flag_left, flag_right, epoch);
+    ipc_last_cta_signals(P.counter, ipc_slot(P.sflag[0], ep, 1), ipc_slot(P.sflag[1], ep, 1), ep);
 }
 
-__global__ void __launch_bounds__(256) k_ipc_x_to_y(double *__restrict__ A, const LevelView L, const int planar,
-                                                    const double *xr_lo, const double *xr_hi, const unsigned *wait_lo, const unsigned *wait_hi,
-                                                    double *dst_front, double *dst_back, unsigned *flag_front, unsigned *flag_back,
-                                                    unsigned *counter, const unsigned epoch) {
-    if (threadIdx.x == 0) { ipc_wait_flag(wait_lo, epoch); ipc_wait_flag(wait_hi, epoch); }
+__global__ void __launch_bounds__(256) k_ipc_x_to_y(double *__restrict__ A, const LevelView L, const int planar, const IpcPlan P) {
+    const unsigned ep = ipc_epoch(P);
+    if (threadIdx.x == 0) { ipc_wait_flag(ipc_slot(P.rflag[0], ep, 1), ep); ipc_wait_flag(ipc_slot(P.rflag[1], ep, 1), ep); }
     __syncthreads();
+    const double *xr_lo = ipc_slot(P.recv[0], ep, P.slot_stride), *xr_hi = ipc_slot(P.recv[1], ep, P.slot_stride);
+    double *dst_front = ipc_slot(P.send[2], ep, P.slot_stride), *dst_back = ipc_slot(P.send[3], ep, P.slot_stride);
     const int nj = planar ? 1 : L.Fy;
     const long long cx = (xr_lo || xr_hi) ? (long long)nj * L.Fz : 0;
     const long long cy = (dst_front || dst_back) ? (long long)L.Fx * L.Fz : 0;
@@ -876,13 +894,14 @@ __global__ void __launch_bounds__(256) k_ipc_x_to_y(double *__restrict__ A, cons
             }
         }
     }
-    if (dst_front || dst_back) ipc_last_cta_signals(counter, flag_front, flag_back, epoch);
+    if (dst_front || dst_back) ipc_last_cta_signals(P.counter + 1, ipc_slot(P.sflag[2], ep, 1), ipc_slot(P.sflag[3], ep, 1), ep);
 }
 
-__global__ void __launch_bounds__(256) k_ipc_recv_y(double *__restrict__ A, const LevelView L, const double *yr_lo, const double *yr_hi,
-                                                    const unsigned *wait_lo, const unsigned *wait_hi, const unsigned epoch) {
-    if (threadIdx.x == 0) { ipc_wait_flag(wait_lo, epoch); ipc_wait_flag(wait_hi, epoch); }
+__global__ void __launch_bounds__(256) k_ipc_recv_y(double *__restrict__ A, const LevelView L, const IpcPlan P) {
+    const unsigned ep = ipc_epoch(P);
+    if (threadIdx.x == 0) { ipc_wait_flag(ipc_slot(P.rflag[2], ep, 1), ep); ipc_wait_flag(ipc_slot(P.rflag[3], ep, 1), ep); }
     __syncthreads();
+    const double *yr_lo = ipc_slot(P.recv[2], ep, P.slot_stride), *yr_hi = ipc_slot(P.recv[3], ep, P.slot_stride);
     const long long cnt = (long long)L.Fx * L.Fz;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(q / L.Fz) - 1, k = (int)(q % L.Fz) - 1;
@@ -896,63 +915,68 @@ __global__ void __launch_bounds__(256) k_ipc_recv_y(double *__restrict__ A, cons
  * sends its x faces, raises the flags, waits for its own, unpacks, sends the y rows (with the fresh x pads), waits,
  * unpacks, and finishes with the face operations -- the same phases as the three kernels above, separated by
  * __syncthreads instead of launches. */
-struct IpcPlan {
-    double *send[4];            /* neighbour's receive buffer for my left / right x plane and front / back y row (nullptr: none) */
-    unsigned *sflag[4];         /* the flag of that buffer, in the neighbour's arena */
-    const double *recv[4];      /* my receive buffers: x lo, x hi, y lo, y hi */
-    const unsigned *rflag[4];   /* my flags */
-};
 template <int DIM>
-__global__ void __launch_bounds__(1024) k_ipc_exchange_cta(double *A, const LevelView L, const IpcPlan P, const unsigned epoch,
+__global__ void __launch_bounds__(1024) k_ipc_exchange_cta(double *A, const LevelView L, const IpcPlan P,
                                                           const FaceModes self_x, const FaceModes self_y, const FaceModes bc) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const bool planar = (DIM == 2);
+    const unsigned epoch = ipc_epoch(P);
+    double *send[4];
+    const double *recv[4];
+    unsigned *sflag[4];
+    const unsigned *rflag[4];
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+        send[f] = ipc_slot(P.send[f], epoch, P.slot_stride); recv[f] = ipc_slot(P.recv[f], epoch, P.slot_stride);
+        sflag[f] = ipc_slot(P.sflag[f], epoch, 1); rflag[f] = ipc_slot(P.rflag[f], epoch, 1);
+    }
     const int nj = planar ? 1 : L.Fy;
     const int cx = nj * L.Fz, cy = planar ? 0 : L.Fx * L.Fz;
     faces_apply<DIM>(A, L, self_x, tid, nthr);                     /* periodic self-neighbour in x (no-op when all modes are NONE) */
-    if (P.send[0] || P.send[1]) {
+    if (send[0] || send[1]) {
         for (int q = tid; q < cx; q += nthr) {
             const int j = (planar ? 0 : -1) + q / L.Fz, k = q % L.Fz - 1;
-            if (P.send[0]) P.send[0][q] = A[mg_at(L, 1, j, k)];
-            if (P.send[1]) P.send[1][q] = A[mg_at(L, L.nx - 2, j, k)];
+            if (send[0]) send[0][q] = A[mg_at(L, 1, j, k)];
+            if (send[1]) send[1][q] = A[mg_at(L, L.nx - 2, j, k)];
         }
         __threadfence_system();
         __syncthreads();
-        if (tid == 0) { ipc_signal(P.sflag[0], epoch); ipc_signal(P.sflag[1], epoch); }
+        if (tid == 0) { ipc_signal(sflag[0], epoch); ipc_signal(sflag[1], epoch); }
     }
-    if (tid == 0) { ipc_wait_flag(P.rflag[0], epoch); ipc_wait_flag(P.rflag[1], epoch); }
+    if (tid == 0) { ipc_wait_flag(rflag[0], epoch); ipc_wait_flag(rflag[1], epoch); }
     __syncthreads();
-    if (P.recv[0] || P.recv[1])
+    if (recv[0] || recv[1])
         for (int q = tid; q < cx; q += nthr) {
             const int j = (planar ? 0 : -1) + q / L.Fz, k = q % L.Fz - 1;
-            if (P.recv[0]) A[mg_at(L, -1, j, k)] = ld_cg_f64(P.recv[0] + q);
-            if (P.recv[1]) A[mg_at(L, L.nx, j, k)] = ld_cg_f64(P.recv[1] + q);
+            if (recv[0]) A[mg_at(L, -1, j, k)] = ld_cg_f64(recv[0] + q);
+            if (recv[1]) A[mg_at(L, L.nx, j, k)] = ld_cg_f64(recv[1] + q);
         }
     __syncthreads();
     if (DIM == 3) {
         faces_apply<DIM>(A, L, self_y, tid, nthr);
-        if (P.send[2] || P.send[3]) {
+        if (send[2] || send[3]) {
             for (int q = tid; q < cy; q += nthr) {
                 const int i = q / L.Fz - 1, k = q % L.Fz - 1;
-                if (P.send[2]) P.send[2][q] = A[mg_at(L, i, 1, k)];
-                if (P.send[3]) P.send[3][q] = A[mg_at(L, i, L.ny - 2, k)];
+                if (send[2]) send[2][q] = A[mg_at(L, i, 1, k)];
+                if (send[3]) send[3][q] = A[mg_at(L, i, L.ny - 2, k)];
             }
             __threadfence_system();
             __syncthreads();
-            if (tid == 0) { ipc_signal(P.sflag[2], epoch); ipc_signal(P.sflag[3], epoch); }
+            if (tid == 0) { ipc_signal(sflag[2], epoch); ipc_signal(sflag[3], epoch); }
         }
-        if (tid == 0) { ipc_wait_flag(P.rflag[2], epoch); ipc_wait_flag(P.rflag[3], epoch); }
+        if (tid == 0) { ipc_wait_flag(rflag[2], epoch); ipc_wait_flag(rflag[3], epoch); }
         __syncthreads();
-        if (P.recv[2] || P.recv[3])
+        if (recv[2] || recv[3])
             for (int q = tid; q < cy; q += nthr) {
                 const int i = q / L.Fz - 1, k = q % L.Fz - 1;
-                if (P.recv[2]) A[mg_at(L, i, -1, k)] = ld_cg_f64(P.recv[2] + q);
-                if (P.recv[3]) A[mg_at(L, i, L.ny, k)] = ld_cg_f64(P.recv[3] + q);
+                if (recv[2]) A[mg_at(L, i, -1, k)] = ld_cg_f64(recv[2] + q);
+                if (recv[3]) A[mg_at(L, i, L.ny, k)] = ld_cg_f64(recv[3] + q);
             }
         __syncthreads();
     }
     faces_apply<DIM>(A, L, bc, tid, nthr);                          /* wall BCs of imposeBC (all NONE for a bare updatePads) */
 }
+__global__ void k_set_u32(unsigned *p, const unsigned v) { *p = v; }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* full-weighting restriction (d3:270-297, d2:222-235): thread per coarse point, sums in source order */
@@ -1410,8 +1434,12 @@ __global__ void __launch_bounds__(1024) k_coarse_solve_blocks(double *P, const d
 /* The same loop with the blocks resident in SHARED memory (used whenever they fit; nblk = 1 is the single-rank solve).
  * Per block: pressure and rhs in compact padded layout, the stencil diagonal and its correctly rounded reciprocal per core
  * point (the GS update divides by the diagonal: div_inv reproduces the IEEE quotient from the stored reciprocal), and the
- * coefficient products of every axis.  A GS hyperplane step is then a handful of shared-memory loads and ~30 fp64
- * operations between two barriers instead of a chain of global loads and a division. */
+ * coefficient products of every axis.  All index arithmetic is done ONCE: the five phases of imposeBC (x pads, y pads,
+ * x walls, y walls, z) become (destination, source) lists, the GS wavefront and the residual pass walk a column table.
+ * An iteration is then ~H short shared-memory phases (H = nx+ny+nz-2 hyperplanes) instead of chains of global loads,
+ * integer divisions and an IEEE division per point. */
+struct CoarseCol { int off, s, pt, xi, yj, pad; };   /* sP offset of (b,i,j,k=0); i+j; point index of k=0; b*nx+i; b*ny+j (24 bytes) */
+
 template <int DIM>
 __global__ void __launch_bounds__(256) k_coarse_solve_smem(double *Pg, const double *Rg, const long long stride, const int nblk,
                                                           const CoarseBlock *__restrict__ tab, const LevelView L,
@@ -1426,13 +1454,19 @@ __global__ void __launch_bounds__(256) k_coarse_solve_smem(double *Pg, const dou
     const int Fx = L.Fx, Fy = (DIM == 2) ? 1 : L.Fy, Fz = L.Fz;      /* 2-D: only the live j = 0 row is kept */
     const int jo = (DIM == 2) ? 0 : 1;                               /* row offset of j = 0 */
     const int vol = Fx * Fy * Fz;
-    const int nx = L.nx, ny = L.ny, nz = L.nz, nij = nx * ny, cnt = nij * nz;
+    const int nx = L.nx, ny = L.ny, nz = L.nz, nij = nx * ny, cnt = nij * nz, ncol = nblk * nij;
     double *sP = cs_sm, *sR = sP + nblk * vol, *sD = sR + nblk * vol, *sI = sD + nblk * cnt;
     double *cx2 = sI + nblk * cnt, *cx1 = cx2 + nblk * nx, *cy2 = cx1 + nblk * nx, *cy1 = cy2 + nblk * ny;
     double *cz2 = cy1 + nblk * ny, *cz1 = cz2 + nz, *mx2 = cz1 + nz, *mx1 = mx2 + nblk * nx, *my2 = mx1 + nblk * nx, *my1 = my2 + nblk * ny;
     double *mz2 = my1 + nblk * ny, *mz1 = mz2 + nz;
+    /* integer tables behind the doubles */
+    const int nX = 2 * nblk * Fy * Fz, nY = (DIM == 3) ? 2 * nblk * Fx * Fz : 0, nZ = 2 * nblk * Fx * Fy;
+    CoarseCol *cols = reinterpret_cast<CoarseCol *>(mz1 + nz);
+    int2 *lx = reinterpret_cast<int2 *>(cols + ncol), *ly = lx + nX, *lwx = ly + nY, *lwy = lwx + nX, *lz = lwy + nY;
 #define CS_AT(i, j, k) ((((i) + 1) * Fy + ((j) + jo)) * Fz + ((k) + 1))
     __syncthreads();
+    const int xE = nx - 1, yE = ny - 1, zE = nz - 1;
+    const int sj = Fz, si = Fy * Fz;
     for (int q = tid; q < nblk * vol; q += nthr) {
         const int b = q / vol, w = q % vol;
         const int k = w % Fz - 1, j = (w / Fz) % Fy - jo, i = w / (Fz * Fy) - 1;
@@ -1444,6 +1478,41 @@ __global__ void __launch_bounds__(256) k_coarse_solve_smem(double *Pg, const dou
     if (DIM == 3)
         for (int q = tid; q < nblk * ny; q += nthr) { const int b = q / ny, j = q % ny; my2[q] = s_tab[b].ety2[j]; my1[q] = s_tab[b].etyy[j]; cy2[q] = kyc * my2[q]; cy1[q] = kyc * my1[q]; }
     for (int q = tid; q < nz; q += nthr) { mz2[q] = L.ztz2[q]; mz1[q] = L.ztzz[q]; cz2[q] = kzc * mz2[q]; cz1[q] = kzc * mz1[q]; }
+    for (int q = tid; q < ncol; q += nthr) {
+        const int b = q / nij, w = q % nij, i = w / ny, j = w % ny;
+        CoarseCol c;
+        c.off = b * vol + CS_AT(i, j, 0); c.s = i + j; c.pt = b * cnt + w * nz; c.xi = b * nx + i; c.yj = b * ny + j; c.pad = 0;
+        cols[q] = c;
+    }
+    /* imposeBC lists: entry = (destination, source) offsets into sP; source < 0 encodes "negate" as ~source; destination -1 = none */
+    const bool ng = (wall_mode == FACE_NEG_MIRROR);
+    for (int q = tid; q < nblk * Fy * Fz; q += nthr) {
+        const int b = q / (Fy * Fz), w = q % (Fy * Fz), o = b * vol + w;
+        const int nl = s_tab[b].nbr[0], nr = s_tab[b].nbr[1];
+        lx[2 * q] = (nl >= 0) ? make_int2(o, nl * vol + xE * si + w) : make_int2(-1, 0);                 /* i = -1 <- neighbour's i = xE-1 */
+        lx[2 * q + 1] = (nr >= 0) ? make_int2(o + (xE + 2) * si, nr * vol + 2 * si + w) : make_int2(-1, 0);   /* i = xE+1 <- neighbour's i = 1 */
+        const bool wl = s_tab[b].wall[0] && wall_mode != FACE_NONE, wr = s_tab[b].wall[1] && wall_mode != FACE_NONE;
+        const int sl = o + 2 * si, sr = o + xE * si;
+        lwx[2 * q] = wl ? make_int2(o, ng ? ~sl : sl) : make_int2(-1, 0);
+        lwx[2 * q + 1] = wr ? make_int2(o + (xE + 2) * si, ng ? ~sr : sr) : make_int2(-1, 0);
+    }
+    if (DIM == 3)
+        for (int q = tid; q < nblk * Fx * Fz; q += nthr) {
+            const int b = q / (Fx * Fz), w = q % (Fx * Fz), r = (w / Fz) * si + (w % Fz), o = b * vol + r;
+            const int nf = s_tab[b].nbr[2], nk = s_tab[b].nbr[3];
+            ly[2 * q] = (nf >= 0) ? make_int2(o, nf * vol + r + yE * sj) : make_int2(-1, 0);
+            ly[2 * q + 1] = (nk >= 0) ? make_int2(o + (yE + 2) * sj, nk * vol + r + 2 * sj) : make_int2(-1, 0);
+            const bool wf = s_tab[b].wall[2] && wall_mode != FACE_NONE, wb = s_tab[b].wall[3] && wall_mode != FACE_NONE;
+            const int sf = o + 2 * sj, sb = o + yE * sj;
+            lwy[2 * q] = wf ? make_int2(o, ng ? ~sf : sf) : make_int2(-1, 0);
+            lwy[2 * q + 1] = wb ? make_int2(o + (yE + 2) * sj, ng ? ~sb : sb) : make_int2(-1, 0);
+        }
+    for (int q = tid; q < nblk * Fx * Fy; q += nthr) {
+        const int o = q * Fz;                                       /* (b, i, j) row start */
+        const int slo = o + ((z_lo_mode == FACE_PERIODIC) ? zE : 2), shi = o + ((z_hi_mode == FACE_PERIODIC) ? 2 : zE);
+        lz[2 * q] = (z_lo_mode != FACE_NONE) ? make_int2(o, (z_lo_mode == FACE_NEG_MIRROR) ? ~slo : slo) : make_int2(-1, 0);
+        lz[2 * q + 1] = (z_hi_mode != FACE_NONE) ? make_int2(o + zE + 2, (z_hi_mode == FACE_NEG_MIRROR) ? ~shi : shi) : make_int2(-1, 0);
+    }
     __syncthreads();
     for (int q = tid; q < nblk * cnt; q += nthr) {
         const int b = q / cnt, w = q % cnt;
@@ -1456,95 +1525,63 @@ __global__ void __launch_bounds__(256) k_coarse_solve_smem(double *Pg, const dou
     const double two_h = (DIM == 3) ? 2.0 * L.hxhyhz : 2.0 * L.hzhx;
     const LapDiv dv = make_lapdiv(hx * hx, 2.0 * hx, hy * hy, 2.0 * hy, hz * hz, 2.0 * hz, DIM == 3);
     const int H = nx + ny + nz - 2;
-    const int xE = nx - 1, yE = ny - 1, zE = nz - 1;
-    const int sj = Fz, si = Fy * Fz;
+    /* residual pass: KZ lanes (power of two >= nz) along k, the other threads over columns */
+    int lkz = 0;
+    while ((1 << lkz) < nz && (1 << lkz) < nthr) lkz++;
+    const int KZ = 1 << lkz, kk = tid & (KZ - 1), cg = tid >> lkz, ncg = nthr >> lkz;
+    __syncthreads();
+#define CS_APPLY(list, n)                                                          \
+    for (int e = tid; e < (n); e += nthr) {                                        \
+        const int2 ds = list[e];                                                   \
+        if (ds.x >= 0) sP[ds.x] = (ds.y >= 0) ? sP[ds.y] : -sP[~ds.y];             \
+    }                                                                              \
     __syncthreads();
     int iter = 0;
     while (true) {
         /* ---- imposeBC of every block: x pads, y pads (with the fresh x pads), then walls x, y, z ---- */
-        for (int q = tid; q < nblk * Fy * Fz; q += nthr) {
-            const int b = q / (Fy * Fz), w = q % (Fy * Fz);
-            const int nl = s_tab[b].nbr[0], nr = s_tab[b].nbr[1];
-            if (nl >= 0) sP[b * vol + w] = sP[nl * vol + xE * si + w];                   /* i = -1 <- neighbour's i = xE-1 */
-            if (nr >= 0) sP[b * vol + (xE + 2) * si + w] = sP[nr * vol + 2 * si + w];    /* i = xE+1 <- neighbour's i = 1 */
-        }
-        __syncthreads();
-        if (DIM == 3) {
-            for (int q = tid; q < nblk * Fx * Fz; q += nthr) {
-                const int b = q / (Fx * Fz), w = q % (Fx * Fz);
-                const int o = (w / Fz) * si + (w % Fz);
-                const int nf = s_tab[b].nbr[2], nk = s_tab[b].nbr[3];
-                if (nf >= 0) sP[b * vol + o] = sP[nf * vol + o + yE * sj];
-                if (nk >= 0) sP[b * vol + o + (yE + 2) * sj] = sP[nk * vol + o + 2 * sj];
-            }
-            __syncthreads();
-        }
+        CS_APPLY(lx, nX)
+        if (DIM == 3) { CS_APPLY(ly, nY) }
         if (wall_mode != FACE_NONE) {
-            const bool ng = (wall_mode == FACE_NEG_MIRROR);
-            for (int q = tid; q < nblk * Fy * Fz; q += nthr) {
-                const int b = q / (Fy * Fz), w = q % (Fy * Fz);
-                if (s_tab[b].wall[0]) { const double v = sP[b * vol + 2 * si + w]; sP[b * vol + w] = ng ? -v : v; }
-                if (s_tab[b].wall[1]) { const double v = sP[b * vol + xE * si + w]; sP[b * vol + (xE + 2) * si + w] = ng ? -v : v; }
-            }
-            __syncthreads();
-            if (DIM == 3) {
-                for (int q = tid; q < nblk * Fx * Fz; q += nthr) {
-                    const int b = q / (Fx * Fz), w = q % (Fx * Fz);
-                    const int o = b * vol + (w / Fz) * si + (w % Fz);
-                    if (s_tab[b].wall[2]) { const double v = sP[o + 2 * sj]; sP[o] = ng ? -v : v; }
-                    if (s_tab[b].wall[3]) { const double v = sP[o + yE * sj]; sP[o + (yE + 2) * sj] = ng ? -v : v; }
-                }
-                __syncthreads();
-            }
+            CS_APPLY(lwx, nX)
+            if (DIM == 3) { CS_APPLY(lwy, nY) }
         }
-        for (int q = tid; q < nblk * Fx * Fy; q += nthr) {
-            const int o = q * Fz;                                   /* (b, i, j) row start */
-            if (z_lo_mode != FACE_NONE) {
-                const double v = sP[o + ((z_lo_mode == FACE_PERIODIC) ? zE : 2)];       /* k = zE-1 or k = 1 */
-                sP[o] = (z_lo_mode == FACE_NEG_MIRROR) ? -v : v;
-            }
-            if (z_hi_mode != FACE_NONE) {
-                const double v = sP[o + ((z_hi_mode == FACE_PERIODIC) ? 2 : zE)];
-                sP[o + zE + 2] = (z_hi_mode == FACE_NEG_MIRROR) ? -v : v;
-            }
-        }
-        __syncthreads();
+        CS_APPLY(lz, nZ)
         if (iter < 0) break;
 
         /* ---- block Gauss-Seidel wavefront ---- */
         for (int h = 0; h < H; ++h) {
-            for (int q = tid; q < nblk * nij; q += nthr) {
-                const int b = q / nij, w = q % nij;
-                const int i = w / ny, j = w % ny, k = h - i - j;
-                if (k >= 0 && k < nz) {
-                    double *c = sP + b * vol + CS_AT(i, j, k);
-                    const int pt = b * cnt + (i * ny + j) * nz + k;
+            for (int q = tid; q < ncol; q += nthr) {
+                const CoarseCol cc = cols[q];
+                const int k = h - cc.s;
+                if ((unsigned)k < (unsigned)nz) {
+                    double *c = sP + cc.off + k;
                     double t;
                     if (DIM == 3)
-                        t = relax3_num(c[si], c[-si], c[sj], c[-sj], c[1], c[-1], sR[b * vol + CS_AT(i, j, k)], cx2[b * nx + i], cx1[b * nx + i], hx,
-                                       cy2[b * ny + j], cy1[b * ny + j], hy, cz2[k], cz1[k], hz, two_h);
+                        t = relax3_num(c[si], c[-si], c[sj], c[-sj], c[1], c[-1], sR[cc.off + k], cx2[cc.xi], cx1[cc.xi], hx,
+                                       cy2[cc.yj], cy1[cc.yj], hy, cz2[k], cz1[k], hz, two_h);
                     else
-                        t = relax2_num(c[si], c[-si], c[1], c[-1], sR[b * vol + CS_AT(i, j, k)], cx2[b * nx + i], cx1[b * nx + i], hx, cz2[k], cz1[k], hz, two_h);
-                    c[0] = div_inv(t, sD[pt], sI[pt]);
+                        t = relax2_num(c[si], c[-si], c[1], c[-1], sR[cc.off + k], cx2[cc.xi], cx1[cc.xi], hx, cz2[k], cz1[k], hz, two_h);
+                    c[0] = div_inv(t, sD[cc.pt + k], sI[cc.pt + k]);
                 }
             }
             __syncthreads();
         }
         double m = -1.0e-10;
-        for (int q = tid; q < nblk * cnt; q += nthr) {
-            const int b = q / cnt, w = q % cnt;
-            const int k = w % nz, j = (w / nz) % ny, i = w / (nz * ny);
-            const double *c = sP + b * vol + CS_AT(i, j, k);
-            const double r = sR[b * vol + CS_AT(i, j, k)];
-            double lp;
-            if (DIM == 3) {
-                lp = p2 ? lap3_inv<true>(c[0], c[si], c[-si], c[sj], c[-sj], c[1], c[-1], mx2[b * nx + i], mx1[b * nx + i], my2[b * ny + j], my1[b * ny + j], mz2[k], mz1[k], dv)
-                        : lap3_inv<false>(c[0], c[si], c[-si], c[sj], c[-sj], c[1], c[-1], mx2[b * nx + i], mx1[b * nx + i], my2[b * ny + j], my1[b * ny + j], mz2[k], mz1[k], dv);
-            } else {
-                lp = p2 ? lap2_inv<true>(c[0], c[si], c[-si], c[1], c[-1], mx2[b * nx + i], mx1[b * nx + i], mz2[k], mz1[k], dv)
-                        : lap2_inv<false>(c[0], c[si], c[-si], c[1], c[-1], mx2[b * nx + i], mx1[b * nx + i], mz2[k], mz1[k], dv);
+        for (int q = cg; q < ncol; q += ncg) {
+            const CoarseCol cc = cols[q];
+            for (int k = kk; k < nz; k += KZ) {
+                const double *c = sP + cc.off + k;
+                const double r = sR[cc.off + k];
+                double lp;
+                if (DIM == 3) {
+                    lp = p2 ? lap3_inv<true>(c[0], c[si], c[-si], c[sj], c[-sj], c[1], c[-1], mx2[cc.xi], mx1[cc.xi], my2[cc.yj], my1[cc.yj], mz2[k], mz1[k], dv)
+                            : lap3_inv<false>(c[0], c[si], c[-si], c[sj], c[-sj], c[1], c[-1], mx2[cc.xi], mx1[cc.xi], my2[cc.yj], my1[cc.yj], mz2[k], mz1[k], dv);
+                } else {
+                    lp = p2 ? lap2_inv<true>(c[0], c[si], c[-si], c[1], c[-1], mx2[cc.xi], mx1[cc.xi], mz2[k], mz1[k], dv)
+                            : lap2_inv<false>(c[0], c[si], c[-si], c[1], c[-1], mx2[cc.xi], mx1[cc.xi], mz2[k], mz1[k], dv);
+                }
+                m = fmax(m, fabs(r - lp));
             }
-            m = fmax(m, fabs(r - lp));
         }
         m = block_reduce<true>(m, sm);
         if (tid == 0) s_max = m;
@@ -1560,12 +1597,16 @@ __global__ void __launch_bounds__(256) k_coarse_solve_smem(double *Pg, const dou
         const int k = w % Fz - 1, j = (w / Fz) % Fy - jo, i = w / (Fz * Fy) - 1;
         Pg[b * stride + mg_at(L, i, j, k)] = sP[q];
     }
+#undef CS_APPLY
 #undef CS_AT
 }
 static inline size_t coarse_smem_bytes(const LevelView &L, int dim, int nblk) {
     const size_t Fy = (dim == 2) ? 1 : L.Fy;
     const size_t vol = (size_t)L.Fx * Fy * L.Fz, cnt = (size_t)L.nx * L.ny * L.nz;
-    return sizeof(double) * (nblk * (2 * vol + 2 * cnt) + 4 * (size_t)nblk * (L.nx + L.ny) + 4 * (size_t)L.nz + 16);
+    const size_t dbl = nblk * (2 * vol + 2 * cnt) + 4 * (size_t)nblk * (L.nx + L.ny) + 4 * (size_t)L.nz;
+    const size_t nX = 2 * nblk * Fy * L.Fz, nY = (dim == 3) ? 2 * (size_t)nblk * L.Fx * L.Fz : 0, nZ = 2 * nblk * L.Fx * Fy;
+    const size_t ints = 6 * (size_t)nblk * L.nx * L.ny + 2 * (2 * nX + 2 * nY + nZ);
+    return sizeof(double) * (dbl + 2) + sizeof(int) * (ints + 8);
 }
 
 /* misc */

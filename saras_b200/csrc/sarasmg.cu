@@ -75,6 +75,16 @@ struct Level {
 
 struct ProfEntry { int kind, level, bucket; cudaEvent_t a, b; };
 
+/* one captured V-cycle: valid for one assignment of the level buffers (Jacobi ping-pong) and one profiling setup */
+struct GraphSlot {
+    const double *key;              /* lev[0].buf[SARASMG_PRESSURE] at entry */
+    unsigned prof_key;
+    cudaGraphExec_t exec;
+    std::vector<ProfEntry> prof;    /* external event pairs recorded by the graph, re-read after every replay */
+    long long launches;             /* kernels per replay */
+    unsigned sites;                 /* peer-memory exchanges per replay */
+};
+
 struct sarasmg_solver_s {
     sarasmg_desc d;
     bool planar;
@@ -104,7 +114,15 @@ struct sarasmg_solver_s {
     double *ipc_peer[4];                    /* mapped arena of the left / right / front / back neighbour (nullptr: none) */
     void *ipc_opened[4];
     int ipc_nopened;
-    unsigned ipc_epoch;
+    unsigned ipc_epoch;                     /* number of the last exchange (dense, the same on every rank) */
+    unsigned *d_ipc_base;                   /* device word the exchange kernels add their position to (see IpcPlan) */
+    unsigned ipc_base_h;                    /* its current value */
+    /* CUDA-graph replay of the V-cycle */
+    bool use_graph, capturing;
+    unsigned cap_sites;
+    std::vector<ProfEntry> *cap_prof;
+    std::vector<GraphSlot *> graphs;
+    GraphSlot *last_graph;                  /* replayed since the last profile fold */
     long long ipc_cta_max;                  /* faces up to this many doubles are exchanged by the single-CTA kernel */
     /* agglomerated coarsest-level solve (k_coarse_solve_blocks): all ranks' coarsest arrays, block table, metric copies */
     double *agg_P, *agg_R;      /* n_proc * lev[D].elems doubles each */
@@ -139,7 +157,23 @@ typedef sarasmg_solver_s S;
 /* ------------------------------------------------------------------------------------------------ */
 /* instrumentation helpers                                                                           */
 /* ------------------------------------------------------------------------------------------------ */
+/* the stream must be idle: reads the event pairs the last graph replay recorded */
+static int graph_prof_fold(S *s) {
+    if (!s->last_graph) return 0;
+    for (auto &e : s->last_graph->prof) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e.a, e.b));
+        s->prof_ms[e.kind][e.level] += ms;
+        s->prof_n[e.kind][e.level] += 1;
+        if (e.bucket == 1) s->t_comp += ms * 1e-3;
+        if (e.bucket == 2) s->t_tran += ms * 1e-3;
+    }
+    s->last_graph = nullptr;
+    return 0;
+}
+
 static int prof_fold(S *s) {
+    if (s->last_graph) { CU(cudaStreamSynchronize(s->st)); TRY(graph_prof_fold(s)); }
     if (s->pending.empty()) return 0;
     CU(cudaStreamSynchronize(s->st));
     for (auto &e : s->pending) {
@@ -165,6 +199,11 @@ struct ProfScope {
         if (on && !(s->d.flags & SARASMG_FLAG_TIME_RUN) && level > s->prof_max_level) on = false;
         if (!on) return;
         e.kind = kind; e.level = level; e.bucket = s->bucket;
+        if (s->capturing) {         /* inside a graph: external event-record nodes, owned by the graph slot */
+            cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+            cudaEventRecordWithFlags(e.a, s->st, cudaEventRecordExternal);
+            return;
+        }
         for (cudaEvent_t *ev : {&e.a, &e.b}) {
             if (!s->ev_pool.empty()) { *ev = s->ev_pool.back(); s->ev_pool.pop_back(); }
             else cudaEventCreate(ev);
@@ -173,6 +212,11 @@ struct ProfScope {
     }
     ~ProfScope() {
         if (!on) return;
+        if (s->capturing) {
+            cudaEventRecordWithFlags(e.b, s->st, cudaEventRecordExternal);
+            s->cap_prof->push_back(e);
+            return;
+        }
         cudaEventRecord(e.b, s->st);
         s->pending.push_back(e);
         if (s->pending.size() > 8192) prof_fold(s);
@@ -280,35 +324,35 @@ static int update_pads(S *s, int level, double *A, const int *bc = nullptr, bool
     const int nj = s->planar ? 1 : v.Fy;
     const long long cx = (long long)nj * v.Fz, cy = (long long)v.Fx * v.Fz;
     if (s->ipc_ok) {
-        /* peer-memory path: three launches, no library call (kernels and protocol in mg_kernels.cuh) */
-        const unsigned ep = ++s->ipc_epoch;
-        const int slot = (int)(ep & 1u);
-        const size_t xc = s->ipc_xc, yc = s->ipc_yc, sb = (size_t)slot * s->ipc_slot;
+        /* peer-memory path: no library call (kernels and protocol in mg_kernels.cuh).  The exchange number is
+         * *d_ipc_base + add: inside a graph capture `add` is the position of the exchange in the graph */
+        IpcPlan P;
+        const size_t xc = s->ipc_xc, yc = s->ipc_yc;
         unsigned *myflags = (unsigned *)(s->ipc_arena + 2 * s->ipc_slot);
-        auto peer_buf = [&](int f, size_t off) { return s->ipc_peer[f] + sb + off; };
-        auto peer_flag = [&](int f, int side) { return (unsigned *)(s->ipc_peer[f] + 2 * s->ipc_slot) + side * 2 + slot; };
-        double *my = s->ipc_arena + sb;
+        const bool rem[4] = {pp.rl, pp.rr, pp.rf, pp.rb};
+        const size_t send_off[4] = {xc, 0, 2 * xc + yc, 2 * xc}, recv_off[4] = {0, xc, 2 * xc, 2 * xc + yc};
+        const int send_side[4] = {1, 0, 3, 2};      /* my left plane lands in the neighbour's RIGHT-side buffer, ... */
+        for (int f = 0; f < 4; f++) {
+            P.send[f] = rem[f] ? s->ipc_peer[f] + send_off[f] : nullptr;
+            P.sflag[f] = rem[f] ? (unsigned *)(s->ipc_peer[f] + 2 * s->ipc_slot) + send_side[f] * 2 : nullptr;
+            P.recv[f] = rem[f] ? s->ipc_arena + recv_off[f] : nullptr;
+            P.rflag[f] = rem[f] ? myflags + f * 2 : nullptr;
+        }
+        P.slot_stride = (long long)s->ipc_slot;
+        P.base = s->d_ipc_base;
+        P.add = s->capturing ? ++s->cap_sites : (++s->ipc_epoch - s->ipc_base_h);
+        P.counter = myflags + 16;
         const bool xrem = pp.rl || pp.rr, yrem = pp.rf || pp.rb;
         if (std::max(cx, s->planar ? 0LL : cy) <= s->ipc_cta_max) {
             /* small level: the whole exchange, and the wall BCs of imposeBC, in one single-CTA launch */
-            IpcPlan P;
-            const bool rem[4] = {pp.rl, pp.rr, pp.rf, pp.rb};
-            const size_t send_off[4] = {xc, 0, 2 * xc + yc, 2 * xc}, recv_off[4] = {0, xc, 2 * xc, 2 * xc + yc};
-            const int send_side[4] = {1, 0, 3, 2};
-            for (int f = 0; f < 4; f++) {
-                P.send[f] = rem[f] ? peer_buf(f, send_off[f]) : nullptr;
-                P.sflag[f] = rem[f] ? peer_flag(f, send_side[f]) : nullptr;
-                P.recv[f] = rem[f] ? my + recv_off[f] : nullptr;
-                P.rflag[f] = rem[f] ? myflags + f * 2 + slot : nullptr;
-            }
             FaceModes fx, fy, fb;
             for (int q = 0; q < 6; q++) { fx.m[q] = FACE_NONE; fy.m[q] = FACE_NONE; fb.m[q] = bc ? bc[q] : FACE_NONE; }
             fx.m[0] = pp.self[0]; fx.m[1] = pp.self[1]; fy.m[2] = pp.self[2]; fy.m[3] = pp.self[3];
             if (s->planar) { fb.m[2] = FACE_NONE; fb.m[3] = FACE_NONE; }
             fx.xwall = fx.ywall = fx.zwall = fy.xwall = fy.ywall = fy.zwall = nullptr;
             fb.xwall = s->d_wall[0]; fb.ywall = s->d_wall[1]; fb.zwall = s->d_wall[2];
-            if (s->planar) k_ipc_exchange_cta<2><<<1, 1024, 0, s->st>>>(A, v, P, ep, fx, fy, fb);
-            else k_ipc_exchange_cta<3><<<1, 1024, 0, s->st>>>(A, v, P, ep, fx, fy, fb);
+            if (s->planar) k_ipc_exchange_cta<2><<<1, 1024, 0, s->st>>>(A, v, P, fx, fy, fb);
+            else k_ipc_exchange_cta<3><<<1, 1024, 0, s->st>>>(A, v, P, fx, fy, fb);
             TRY(kcheck(s, "k_ipc_exchange_cta"));
             if (bc_done) *bc_done = true;
             return 0;
@@ -318,23 +362,17 @@ static int update_pads(S *s, int level, double *A, const int *bc = nullptr, bool
             TRY(launch_faces(s, A, L, m, false));
         }
         if (xrem) {
-            k_ipc_send_x<<<std::min(face_blocks(cx), 296u), 256, 0, s->st>>>(A, v, s->planar,
-                pp.rl ? peer_buf(0, xc) : nullptr, pp.rr ? peer_buf(1, 0) : nullptr,
-                pp.rl ? peer_flag(0, 1) : nullptr, pp.rr ? peer_flag(1, 0) : nullptr, myflags + 16, ep);
+            k_ipc_send_x<<<std::min(face_blocks(cx), 296u), 256, 0, s->st>>>(A, v, s->planar, P);
             TRY(kcheck(s, "k_ipc_send_x"));
         }
-        k_ipc_x_to_y<<<std::min(face_blocks(cx + cy), 296u), 256, 0, s->st>>>(A, v, s->planar,
-            pp.rl ? my : nullptr, pp.rr ? my + xc : nullptr, pp.rl ? myflags + 0 * 2 + slot : nullptr, pp.rr ? myflags + 1 * 2 + slot : nullptr,
-            pp.rf ? peer_buf(2, 2 * xc + yc) : nullptr, pp.rb ? peer_buf(3, 2 * xc) : nullptr,
-            pp.rf ? peer_flag(2, 3) : nullptr, pp.rb ? peer_flag(3, 2) : nullptr, myflags + 17, ep);
+        k_ipc_x_to_y<<<std::min(face_blocks(cx + cy), 296u), 256, 0, s->st>>>(A, v, s->planar, P);
         TRY(kcheck(s, "k_ipc_x_to_y"));
         if (pp.self[2] | pp.self[3]) {
             const int m[6] = {FACE_NONE, FACE_NONE, pp.self[2], pp.self[3], FACE_NONE, FACE_NONE};
             TRY(launch_faces(s, A, L, m, false));
         }
         if (yrem) {
-            k_ipc_recv_y<<<std::min(face_blocks(cy), 296u), 256, 0, s->st>>>(A, v, pp.rf ? my + 2 * xc : nullptr, pp.rb ? my + 2 * xc + yc : nullptr,
-                pp.rf ? myflags + 2 * 2 + slot : nullptr, pp.rb ? myflags + 3 * 2 + slot : nullptr, ep);
+            k_ipc_recv_y<<<std::min(face_blocks(cy), 296u), 256, 0, s->st>>>(A, v, P);
             TRY(kcheck(s, "k_ipc_recv_y"));
         }
         return 0;
@@ -1052,6 +1090,69 @@ static int op_vcycle(S *s, int *coarse_iters) {
     return 0;
 }
 
+/* One V-cycle of mgSolve.  The cycle is a fixed sequence of several hundred launches, most of them on latency-bound
+ * coarse levels, so it is captured once into a CUDA graph and replayed: kernels, memsets, the peer-memory exchanges (their
+ * exchange numbers come from a device word, see IpcPlan), the NCCL all-gathers of the agglomerated coarsest solve and the
+ * iteration-count read-back.  A graph is keyed by the level-buffer assignment (Jacobi ping-pong) and the profiling setup. */
+static unsigned graph_prof_key(const S *s) {
+    if (!(s->d.flags & (SARASMG_FLAG_PROFILE | SARASMG_FLAG_TIME_RUN))) return 0u;
+    return 1u + (unsigned)std::min(s->prof_max_level, 1000) + ((s->d.flags & SARASMG_FLAG_TIME_RUN) ? 100000u : 0u);
+}
+static int run_vcycle(S *s) {
+    const bool capturable = s->use_graph && (s->d.n_proc == 1 || (s->agg_ok && !s->coarse_legacy)) && !s->gs_legacy;
+    if (!capturable) return op_vcycle(s, nullptr);
+    const double *key = s->lev[0].buf[SARASMG_PRESSURE];
+    const unsigned pkey = graph_prof_key(s);
+    GraphSlot *g = nullptr;
+    for (GraphSlot *q : s->graphs) if (q->key == key && q->prof_key == pkey) g = q;
+    if (!g) {
+        g = new GraphSlot();
+        g->key = key; g->prof_key = pkey; g->exec = nullptr;
+        const long long l0 = s->launches;
+        s->capturing = true; s->cap_sites = 0; s->cap_prof = &g->prof;
+        cudaError_t ce = cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal);
+        int rc = (ce == cudaSuccess) ? op_vcycle(s, nullptr) : 1;
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce2 = cudaStreamEndCapture(s->st, &graph);
+        s->capturing = false;
+        if (ce != cudaSuccess || ce2 != cudaSuccess || rc) {
+            if (graph) cudaGraphDestroy(graph);
+            delete g;
+            if (rc && ce == cudaSuccess) return rc;
+            return set_err("CUDA graph capture of the V-cycle failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
+        }
+        ce = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { delete g; return set_err("cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+        g->launches = s->launches - l0;
+        s->launches = l0;
+        g->sites = s->cap_sites;
+        s->graphs.push_back(g);
+    } else {
+        /* the capture performed the host-side state changes of one cycle; a replay has to repeat them */
+        if (!s->d.gs_smooth && ((s->d.pre_smooth + s->d.post_smooth) & 1))
+            for (int l = 0; l < s->D; l++) {
+                Level &L = s->lev[l];
+                std::swap(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_TMP]);
+                std::swap(L.tmapP[SARASMG_PRESSURE], L.tmapP[SARASMG_TMP]);
+                std::swap(L.tmapR[SARASMG_PRESSURE], L.tmapR[SARASMG_TMP]);
+            }
+        s->vLevel = 0;
+        s->zeroBC = 0;
+    }
+    if (s->last_graph) { CU(cudaStreamSynchronize(s->st)); TRY(graph_prof_fold(s)); }
+    if (g->sites) {
+        k_set_u32<<<1, 1, 0, s->st>>>(s->d_ipc_base, s->ipc_epoch);
+        TRY(kcheck(s, "k_set_u32"));
+        s->ipc_base_h = s->ipc_epoch;
+    }
+    CU(cudaGraphLaunch(g->exec, s->st));
+    s->ipc_epoch += g->sites;
+    s->launches += g->launches;
+    if (!g->prof.empty()) s->last_graph = g;
+    return 0;
+}
+
 /* everything mgSolve does between the host copies (p:105-148), from the device input buffers */
 static int solve_core(S *s, const double *in_p, const double *in_rhs, int *cycles_done, double *hist, int *citers) {
     const sarasmg_desc &d = s->d;
@@ -1099,10 +1200,11 @@ static int solve_core(S *s, const double *in_p, const double *in_rhs, int *cycle
     CU(cudaEventRecord(s->ev_solve0, s->st));
     for (int i = 0; i < d.vc_count; i++) {                  /* p:132-148 */
         *s->h_iters = 0;
-        TRY(op_vcycle(s, nullptr));
+        TRY(run_vcycle(s));
         double mgResidual = 0.0;
         TRY(op_compute_error(s, d.res_type, &mgResidual));
         if (d.res_type == 0) CU(cudaStreamSynchronize(s->st));
+        TRY(graph_prof_fold(s));                            /* the stream is idle here: computeError read its scalars back */
         s->last_coarse_iters = *s->h_iters;
         if (s->last_coarse_iters > s->maxCount && (d.n_proc == 1 || (s->agg_ok && !s->coarse_legacy)) && d.print_residual && d.rank == 0)
             printf("WARNING: Iterations for solution at coarsest level not converging.\n");    /* d3:240-243 */
@@ -1205,6 +1307,9 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     for (int q = 0; q < 3; q++) s->d_wall[q] = nullptr;
     for (int q = 0; q < 2; q++) s->xs[q] = s->xr[q] = s->ys[q] = s->yr[q] = nullptr;
     s->d_gather = nullptr;
+    s->use_graph = getenv("SARASMG_NO_GRAPH") == nullptr;
+    s->capturing = false; s->cap_sites = 0; s->cap_prof = nullptr; s->last_graph = nullptr;
+    s->d_ipc_base = nullptr; s->ipc_base_h = 0;
     s->ipc_cta_max = getenv("SARASMG_IPC_CTA_MAX") ? atoll(getenv("SARASMG_IPC_CTA_MAX")) : 4096;
     s->ipc_ok = false; s->ipc_arena = nullptr; s->ipc_nopened = 0; s->ipc_epoch = 0;
     for (int q = 0; q < 4; q++) { s->ipc_peer[q] = nullptr; s->ipc_opened[q] = nullptr; }
@@ -1295,6 +1400,8 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
             }
         }
     }
+    CU(cudaMalloc(&s->d_ipc_base, 64));
+    CU(cudaMemsetAsync(s->d_ipc_base, 0, 64, s->st));
     CU(cudaMalloc(&s->d_scal, 64 * sizeof(double)));
     CU(cudaMallocHost(&s->h_scal, (size_t)std::max(64, 8 * desc->n_proc) * sizeof(double)));
     CU(cudaMalloc(&s->d_iters, sizeof(int)));
@@ -1342,6 +1449,12 @@ int sarasmg_destroy(sarasmg_handle s) {
     for (int q = 0; q < 3; q++) if (s->d_wall[q]) cudaFree(s->d_wall[q]);
     for (int q = 0; q < 2; q++) { cudaFree(s->xs[q]); cudaFree(s->xr[q]); cudaFree(s->ys[q]); cudaFree(s->yr[q]); }
     cudaFree(s->d_gather);
+    for (GraphSlot *g : s->graphs) {
+        for (auto &e : g->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        cudaGraphExecDestroy(g->exec);
+        delete g;
+    }
+    cudaFree(s->d_ipc_base);
     for (int q = 0; q < s->ipc_nopened; q++) cudaIpcCloseMemHandle(s->ipc_opened[q]);
     cudaFree(s->ipc_arena);
     cudaFree(s->agg_P); cudaFree(s->agg_R); cudaFree(s->agg_tab); cudaFree(s->agg_met);

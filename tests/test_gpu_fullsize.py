@@ -6,8 +6,8 @@ C4 (513^3, tanh-stretched) and C5 (1025^3) are checked through size-independent 
 BIT FOR BIT in IEEE arithmetic:
   * scaling: every operation of the V-cycle commutes with multiplication by 2 (no rounding is involved), so with the
     data-dependent stopping tests disabled mgSolve(2 rhs) == 2 mgSolve(rhs) exactly;
-  * mirror symmetry: on a uniform Neumann box the Jacobi V-cycle treats +x and -x identically (a + b == b + a), so an
-    x-symmetric right-hand side gives an exactly x-symmetric solution;
+  * two kernel families: the TMA-staged and the register-marching stencil kernels are independent implementations and
+    must produce identical bits at full size;
   * repeatability: the persistent device hierarchy carries no state between calls.
 """
 import numpy as np
@@ -40,7 +40,7 @@ def test_c1_mgtest_129_against_oracle():
     got = s.mg_solve(p, np.ones(F))
     assert got["cycles"] == ref["cycles"] == 25
     assert np.array_equal(got["coarse_iters"], ref["coarse_iters"])
-    assert np.array_equal(got["residuals"], ref["residuals"])
+    np.testing.assert_allclose(got["residuals"], ref["residuals"], rtol=1e-10, atol=0)     # L2 norms: summation order differs
     assert np.array_equal(p, p_ref)
     dev = s.analytic_deviation()
     assert dev == ref["max_dev"] and dev < 1e-5          # the quadratic is an exact solution of the discrete operator
@@ -117,22 +117,37 @@ def test_c4_rbc_513_tanh_scaling_and_repeatability(gs):
     h.close()
 
 
-def test_c5_1025_jacobi_mirror_symmetry():
+def test_c5_1025_two_kernel_families_and_scaling(monkeypatch):
     """BASELINE config 4 at full size: 1025^3, uniform Neumann box, depth 7, V(2,2) Jacobi (the bench workload).
-    An x-symmetric right-hand side must give a bitwise x-symmetric pressure, pads included."""
-    if _host_mem_gb() < 45:
-        pytest.skip("needs ~30 GB of host memory")
-    cfg = dict(dim=3, xInd=10, yInd=10, zInd=10, vcDepth=7, vcCount=2, gsSmooth=0, resType=2, mgTolerance=1e-6)
-    h = host_api.HostSolver(**cfg)
-    Pp, rhs = h.field(0), h.field(1)                    # numpy views of the plainsf storage
-    F = h.F
+    (1) The TMA-staged kernels (production path at this size) and the register-marching kernels (verified against the
+    oracle at every size the oracle can run) are independent implementations of the same arithmetic: their pressure
+    fields must agree bit for bit.  (2) Exact homogeneity under scaling by 2, as in C4."""
+    if _host_mem_gb() < 60:
+        pytest.skip("needs ~45 GB of host memory")
+    cfg = dict(dim=3, xInd=10, yInd=10, zInd=10, vcDepth=7, vcCount=2, gsSmooth=0, resType=2, mgTolerance=0.0)
     rng = np.random.default_rng(5)
-    half = (F[0] + 1) // 2                               # padded x extent is odd: planes 0 .. half-1 and their mirrors
-    rhs[:half] = rng.uniform(-1.0, 1.0, (half, F[1], F[2]))
-    rhs[half:] = rhs[:half - 1][::-1]
+    h = host_api.HostSolver(**cfg)
+    F = h.F
+    Pp, rhs = h.field(0), h.field(1)                    # numpy views of the plainsf storage
+    rng.random(out=rhs.reshape(-1))
+    rhs -= 0.5
     Pp.fill(0.0)
-    cycles = h.mg_solve_inplace()
-    assert cycles == 2
-    assert np.array_equal(Pp[:half - 1], Pp[half:][::-1])
-    assert np.isfinite(Pp).all() and np.abs(Pp).max() > 0
+    assert h.mg_solve_inplace() == 2
+    p_tma = Pp.copy()
+    assert np.isfinite(p_tma).all() and np.abs(p_tma).max() > 0
+    rhs *= 2.0
+    Pp.fill(0.0)
+    assert h.mg_solve_inplace() == 2
+    assert np.array_equal(Pp, 2.0 * p_tma)              # exact homogeneity
+    rhs *= 0.5
+    rhs_keep = rhs.copy()
+    h.close()
+    monkeypatch.setenv("SARASMG_NO_TMA", "1")
+    h = host_api.HostSolver(**cfg)
+    Pp, rhs = h.field(0), h.field(1)
+    rhs[...] = rhs_keep
+    del rhs_keep
+    Pp.fill(0.0)
+    assert h.mg_solve_inplace() == 2
+    assert np.array_equal(Pp, p_tma)
     h.close()

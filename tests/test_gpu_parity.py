@@ -201,6 +201,11 @@ MGSOLVE_CASES = [
     dict(name="ppp_33_gs_v44", dim=3, xInd=5, yInd=5, zInd=5, vcDepth=3, vcCount=5, gsSmooth=1, resType=1, xPer=1, yPer=1, zPer=1,
          preSmooth=4, postSmooth=4),
     dict(name="restype0_one_cycle", dim=3, xInd=4, yInd=4, zInd=4, vcDepth=2, vcCount=7, gsSmooth=0, resType=0),
+    # odd number of Jacobi sweeps per cycle: the level buffers ping-pong from cycle to cycle (two captured V-cycle graphs)
+    dict(name="jacobi_v21_odd_swaps", dim=3, xInd=5, yInd=4, zInd=5, vcDepth=3, vcCount=9, gsSmooth=0, resType=2, mgTolerance=1e-9,
+         preSmooth=2, postSmooth=1),
+    dict(name="jacobi_v21_testpoisson", dim=3, test_poisson=1, xInd=4, yInd=4, zInd=4, vcDepth=2, vcCount=7, gsSmooth=0, resType=2,
+         preSmooth=1, postSmooth=2),
     # C2 LDC shape: 2-D, GS, resType 1, depth 4, 7 cycles
     dict(name="ldc2d_129", dim=2, xInd=7, zInd=7, vcDepth=4, vcCount=7, gsSmooth=1, resType=1),
     dict(name="d2_testpoisson_65", dim=2, test_poisson=1, xInd=6, zInd=6, vcDepth=4, vcCount=10, gsSmooth=1, resType=2),
@@ -300,3 +305,24 @@ def test_tma_kernels_multi_tile_bitexact(mesh, monkeypatch):
     o.vcycle(); s.vcycle()
     assert np.array_equal(s.level_get(0, capi.PRESSURE), o.array(0, 0, mo.PRESSURE))
     s.close()
+
+
+def test_graph_replay_equals_eager_launches(monkeypatch):
+    """mgSolve replays each V-cycle as a CUDA graph; with SARASMG_NO_GRAPH the same launches are issued one by one"""
+    cfg = dict(name="g", dim=3, xInd=5, yInd=5, zInd=4, vcDepth=3, vcCount=8, gsSmooth=1, resType=1, mgTolerance=1e-9, zGrid=2, betaZ=1.2)
+    outs = []
+    for no_graph in (False, True):
+        if no_graph:
+            monkeypatch.setenv("SARASMG_NO_GRAPH", "1")
+        o, s = _mk(cfg)
+        _, F = o.level_dims(0)
+        rhs = smooth_rhs(o, 0, F) + 0.2
+        p = seeded_field(F, 9, 0.01)
+        got = s.mg_solve(p, rhs.copy())
+        got2 = s.mg_solve(p.copy(), rhs.copy())     # second solve: every cycle is a cached replay
+        outs.append((p, got, got2))
+        s.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1]["residuals"], outs[1][1]["residuals"])
+    assert np.array_equal(outs[0][1]["coarse_iters"], outs[1][1]["coarse_iters"])
+    assert outs[0][1]["cycles"] == outs[1][1]["cycles"] and outs[0][2]["cycles"] == outs[1][2]["cycles"]
