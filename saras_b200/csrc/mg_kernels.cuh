@@ -811,12 +811,20 @@ __global__ void __launch_bounds__(256) k_unpack_y2(double *__restrict__ A, const
 /* overwrites a slot I have not consumed.  Data stores are made visible with __threadfence_system() before   */
 /* the last CTA of the grid raises the remote flags; consumers read the buffers with L1-bypassing loads.     */
 /* ------------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ void ipc_wait_flag(const unsigned *flag, const unsigned epoch) {
+/* Bounded spin: a neighbour that never signals (a rank died, or ranks disagree on the exchange count) must not hang the
+ * GPU.  After ~2^25 polls (seconds) the waiter records the exchange number in *err and goes on; the host turns a non-zero
+ * *err into an error at the next synchronisation point. */
+__device__ __forceinline__ void ipc_wait_flag(const unsigned *flag, const unsigned epoch, unsigned *err) {
     if (!flag) return;
+    if (err && *(volatile unsigned *)err) return;          /* an earlier wait already failed: do not stack timeouts */
     unsigned v;
+    unsigned spins = 0;
     do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-    } while ((int)(v - epoch) < 0);
+        if ((int)(v - epoch) >= 0) return;
+        if ((spins & 1023u) == 1023u) __nanosleep(200);
+    } while (++spins < (1u << 25));
+    if (err) atomicMax(err, epoch | 0x80000000u);
 }
 __device__ __forceinline__ void ipc_signal(unsigned *flag, const unsigned epoch) {
     if (flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
@@ -847,6 +855,7 @@ struct IpcPlan {
     const unsigned *base;
     unsigned add;
     unsigned *counter;          /* two arrival counters (x phase, y phase) of the multi-CTA kernels */
+    unsigned *err;              /* device word: set when a wait timed out */
 };
 __device__ __forceinline__ unsigned ipc_epoch(const IpcPlan &P) { return *P.base + P.add; }
 template <typename T>
@@ -867,7 +876,7 @@ __global__ void __launch_bounds__(256) k_ipc_send_x(const double *__restrict__ A
 
 __global__ void __launch_bounds__(256) k_ipc_x_to_y(double *__restrict__ A, const LevelView L, const int planar, const IpcPlan P) {
     const unsigned ep = ipc_epoch(P);
-    if (threadIdx.x == 0) { ipc_wait_flag(ipc_slot(P.rflag[0], ep, 1), ep); ipc_wait_flag(ipc_slot(P.rflag[1], ep, 1), ep); }
+    if (threadIdx.x == 0) { ipc_wait_flag(ipc_slot(P.rflag[0], ep, 1), ep, P.err); ipc_wait_flag(ipc_slot(P.rflag[1], ep, 1), ep, P.err); }
     __syncthreads();
     const double *xr_lo = ipc_slot(P.recv[0], ep, P.slot_stride), *xr_hi = ipc_slot(P.recv[1], ep, P.slot_stride);
     double *dst_front = ipc_slot(P.send[2], ep, P.slot_stride), *dst_back = ipc_slot(P.send[3], ep, P.slot_stride);
@@ -899,7 +908,7 @@ __global__ void __launch_bounds__(256) k_ipc_x_to_y(double *__restrict__ A, cons
 
 __global__ void __launch_bounds__(256) k_ipc_recv_y(double *__restrict__ A, const LevelView L, const IpcPlan P) {
     const unsigned ep = ipc_epoch(P);
-    if (threadIdx.x == 0) { ipc_wait_flag(ipc_slot(P.rflag[2], ep, 1), ep); ipc_wait_flag(ipc_slot(P.rflag[3], ep, 1), ep); }
+    if (threadIdx.x == 0) { ipc_wait_flag(ipc_slot(P.rflag[2], ep, 1), ep, P.err); ipc_wait_flag(ipc_slot(P.rflag[3], ep, 1), ep, P.err); }
     __syncthreads();
     const double *yr_lo = ipc_slot(P.recv[2], ep, P.slot_stride), *yr_hi = ipc_slot(P.recv[3], ep, P.slot_stride);
     const long long cnt = (long long)L.Fx * L.Fz;
@@ -943,7 +952,7 @@ __global__ void __launch_bounds__(1024) k_ipc_exchange_cta(double *A, const Leve
         __syncthreads();
         if (tid == 0) { ipc_signal(sflag[0], epoch); ipc_signal(sflag[1], epoch); }
     }
-    if (tid == 0) { ipc_wait_flag(rflag[0], epoch); ipc_wait_flag(rflag[1], epoch); }
+    if (tid == 0) { ipc_wait_flag(rflag[0], epoch, P.err); ipc_wait_flag(rflag[1], epoch, P.err); }
     __syncthreads();
     if (recv[0] || recv[1])
         for (int q = tid; q < cx; q += nthr) {
@@ -964,7 +973,7 @@ __global__ void __launch_bounds__(1024) k_ipc_exchange_cta(double *A, const Leve
             __syncthreads();
             if (tid == 0) { ipc_signal(sflag[2], epoch); ipc_signal(sflag[3], epoch); }
         }
-        if (tid == 0) { ipc_wait_flag(rflag[2], epoch); ipc_wait_flag(rflag[3], epoch); }
+        if (tid == 0) { ipc_wait_flag(rflag[2], epoch, P.err); ipc_wait_flag(rflag[3], epoch, P.err); }
         __syncthreads();
         if (recv[2] || recv[3])
             for (int q = tid; q < cy; q += nthr) {
@@ -1117,7 +1126,7 @@ __global__ void __launch_bounds__(256) k_prolong_add(const double *__restrict__ 
  * 128-bit store per thread (fine k = 2*k2 sits on a 16-byte boundary), and a warp covers 512 contiguous bytes of each
  * of the four fine rows (2i2 | 2i2+1, 2j2 | 2j2+1).  Sums are left-associated in the order of d3:310-365 / d2:248-270. */
 template <int DIM>
-__global__ void __launch_bounds__(256) k_prolong_march(const double *__restrict__ C, const LevelView Lc, double *__restrict__ Pf,
+__global__ void __launch_bounds__(256) k_prolong_march(const double *__restrict__ C, const LevelView Lc, double *Pf,
                                                        const LevelView Lf, const int ichunk) {
     const int k2 = blockIdx.x * blockDim.x + threadIdx.x;
     const int j2 = (DIM == 3) ? (blockIdx.y * blockDim.y + threadIdx.y) : 0;
@@ -1129,6 +1138,7 @@ __global__ void __launch_bounds__(256) k_prolong_march(const double *__restrict_
     const double *c = C + (long long)(j2 + 1) * Lc.pitch + (k2 + 1 + MG_LEAD);
     double *f = Pf + (long long)((DIM == 3 ? 2 * j2 : 0) + 1) * Lf.pitch + (2 * k2 + 1 + MG_LEAD);
     const int cp = Lc.pitch, fp = Lf.pitch;
+    const long long fplane = Lf.plane;
     /* coarse values: [di][dj][dk] relative to (i2, j2, k2); entries beyond the array edge are never used */
     double a00, a01 = 0.0, a10 = 0.0, a11 = 0.0;        /* plane i2 */
     {
@@ -1137,6 +1147,23 @@ __global__ void __launch_bounds__(256) k_prolong_march(const double *__restrict_
         if (hk) a01 = q[1];
         if (hj) { a10 = q[cp]; if (hk) a11 = q[cp + 1]; }
     }
+    /* The fine array is updated in place, so the compiler may not move a step's loads above the previous step's stores;
+     * the loads of the NEXT step are therefore issued by hand before the stores of this one (two steps of traffic in flight). */
+    auto load_rows = [&](const int i2, double2 (&v)[4]) {           /* rows (2i2, 2j2), (2i2, 2j2+1), (2i2+1, 2j2), (2i2+1, 2j2+1) */
+        const double *fe = f + (long long)(2 * i2 + 1) * fplane;
+        const bool hi = (i2 + 1 < Lc.nx);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            v[r] = make_double2(0.0, 0.0);
+            const bool ok = ((r & 1) == 0 || hj) && (r < 2 || hi);
+            if (ok) {
+                const double *g = fe + (r >> 1) * fplane + (r & 1) * fp;
+                if (hk) v[r] = ld2(g); else v[r].x = g[0];
+            }
+        }
+    };
+    double2 cur[4], nxt[4];
+    load_rows(i0, cur);
     for (int i2 = i0; i2 < i1; ++i2) {
         const bool hi = (i2 + 1 < Lc.nx);               /* fine i = 2*i2+1 exists */
         double b00 = 0.0, b01 = 0.0, b10 = 0.0, b11 = 0.0;   /* plane i2+1 */
@@ -1146,39 +1173,31 @@ __global__ void __launch_bounds__(256) k_prolong_march(const double *__restrict_
             if (hk) b01 = q[1];
             if (hj) { b10 = q[cp]; if (hk) b11 = q[cp + 1]; }
         }
-        double *fe = f + (long long)(2 * i2 + 1) * Lf.plane;         /* fine plane 2*i2 */
-        double *fo = fe + Lf.plane;                                   /* fine plane 2*i2+1 */
-        if (MG_PROLONG_PF > 0 && i2 + MG_PROLONG_PF < i1) {           /* ask L2 for the fine rows of a later step */
-            const double *g = fe + (long long)(2 * MG_PROLONG_PF) * Lf.plane;
-            prefetch_l2(g); prefetch_l2(g + Lf.plane);
-            if (hj) { prefetch_l2(g + fp); prefetch_l2(g + Lf.plane + fp); }
-        }
-        /* even i */
-        {
-            double2 v;
-            v.x = a00;
-            v.y = (a00 + a01) / 2.0;
-            if (hk) { double2 o = ld2(fe); o.x = v.x + o.x; o.y = v.y + o.y; st2(fe, o); } else fe[0] = v.x + fe[0];
-            if (hj) {
-                v.x = (a00 + a10) / 2.0;
-                v.y = (a00 + a01 + a10 + a11) / 4.0;
-                double *g = fe + fp;
-                if (hk) { double2 o = ld2(g); o.x = v.x + o.x; o.y = v.y + o.y; st2(g, o); } else g[0] = v.x + g[0];
-            }
+        if (i2 + 1 < i1) load_rows(i2 + 1, nxt);
+        double *fe = f + (long long)(2 * i2 + 1) * fplane;           /* fine plane 2*i2 */
+        double *fo = fe + fplane;                                     /* fine plane 2*i2+1 */
+        double2 v;
+        v.x = a00;
+        v.y = (a00 + a01) / 2.0;
+        if (hk) st2(fe, make_double2(v.x + cur[0].x, v.y + cur[0].y)); else fe[0] = v.x + cur[0].x;
+        if (hj) {
+            v.x = (a00 + a10) / 2.0;
+            v.y = (a00 + a01 + a10 + a11) / 4.0;
+            if (hk) st2(fe + fp, make_double2(v.x + cur[1].x, v.y + cur[1].y)); else fe[fp] = v.x + cur[1].x;
         }
         if (hi) {
-            double2 v;
             v.x = (a00 + b00) / 2.0;
             v.y = (a00 + a01 + b00 + b01) / 4.0;
-            if (hk) { double2 o = ld2(fo); o.x = v.x + o.x; o.y = v.y + o.y; st2(fo, o); } else fo[0] = v.x + fo[0];
+            if (hk) st2(fo, make_double2(v.x + cur[2].x, v.y + cur[2].y)); else fo[0] = v.x + cur[2].x;
             if (hj) {
                 v.x = (a00 + a10 + b00 + b10) / 4.0;
                 v.y = (a00 + b00 + a10 + a01 + b10 + b01 + a11 + b11) / 8.0;
-                double *g = fo + fp;
-                if (hk) { double2 o = ld2(g); o.x = v.x + o.x; o.y = v.y + o.y; st2(g, o); } else g[0] = v.x + g[0];
+                if (hk) st2(fo + fp, make_double2(v.x + cur[3].x, v.y + cur[3].y)); else fo[fp] = v.x + cur[3].x;
             }
         }
         a00 = b00; a01 = b01; a10 = b10; a11 = b11;
+#pragma unroll
+        for (int r = 0; r < 4; r++) cur[r] = nxt[r];
     }
 }
 

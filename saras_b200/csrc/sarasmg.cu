@@ -118,7 +118,7 @@ struct sarasmg_solver_s {
     unsigned *d_ipc_base;                   /* device word the exchange kernels add their position to (see IpcPlan) */
     unsigned ipc_base_h;                    /* its current value */
     /* CUDA-graph replay of the V-cycle */
-    bool use_graph, capturing;
+    bool use_graph, graph_multi, capturing;
     unsigned cap_sites;
     std::vector<ProfEntry> *cap_prof;
     std::vector<GraphSlot *> graphs;
@@ -342,6 +342,7 @@ static int update_pads(S *s, int level, double *A, const int *bc = nullptr, bool
         P.base = s->d_ipc_base;
         P.add = s->capturing ? ++s->cap_sites : (++s->ipc_epoch - s->ipc_base_h);
         P.counter = myflags + 16;
+        P.err = s->d_ipc_base + 1;
         const bool xrem = pp.rl || pp.rr, yrem = pp.rf || pp.rb;
         if (std::max(cx, s->planar ? 0LL : cy) <= s->ipc_cta_max) {
             /* small level: the whole exchange, and the wall BCs of imposeBC, in one single-CTA launch */
@@ -1090,6 +1091,16 @@ static int op_vcycle(S *s, int *coarse_iters) {
     return 0;
 }
 
+/* after a synchronisation: did a peer-memory wait time out? */
+static int check_ipc_error(S *s) {
+    if (!s->ipc_ok) return 0;
+    unsigned e = 0;
+    CU(cudaMemcpyAsync(&e, s->d_ipc_base + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    if (e) return set_err("peer-memory halo exchange %u timed out on rank %d: a neighbour never signalled (rank lost, or ranks out of step)", e & 0x7fffffffu, s->d.rank);
+    return 0;
+}
+
 /* One V-cycle of mgSolve.  The cycle is a fixed sequence of several hundred launches, most of them on latency-bound
  * coarse levels, so it is captured once into a CUDA graph and replayed: kernels, memsets, the peer-memory exchanges (their
  * exchange numbers come from a device word, see IpcPlan), the NCCL all-gathers of the agglomerated coarsest solve and the
@@ -1099,7 +1110,10 @@ static unsigned graph_prof_key(const S *s) {
     return 1u + (unsigned)std::min(s->prof_max_level, 1000) + ((s->d.flags & SARASMG_FLAG_TIME_RUN) ? 100000u : 0u);
 }
 static int run_vcycle(S *s) {
-    const bool capturable = s->use_graph && (s->d.n_proc == 1 || (s->agg_ok && !s->coarse_legacy)) && !s->gs_legacy;
+    /* several ranks: the graph would hold NCCL all-gathers of the agglomerated coarsest solve; replay works (2 GPUs), but
+     * tearing such a graph down next to its communicator is not validated yet, so it is opt-in (SARASMG_GRAPH_MULTI=1) */
+    const bool capturable = s->use_graph && !s->gs_legacy &&
+                            (s->d.n_proc == 1 || (s->graph_multi && s->agg_ok && !s->coarse_legacy));
     if (!capturable) return op_vcycle(s, nullptr);
     const double *key = s->lev[0].buf[SARASMG_PRESSURE];
     const unsigned pkey = graph_prof_key(s);
@@ -1226,6 +1240,7 @@ static int solve_core(S *s, const double *in_p, const double *in_rhs, int *cycle
     CU(cudaEventElapsedTime(&ms, s->ev_solve0, s->ev_solve1));
     s->last_solve_ms = ms;
     if (cycles_done) *cycles_done = cycles;
+    TRY(check_ipc_error(s));
     return 0;
 }
 
@@ -1308,6 +1323,7 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     for (int q = 0; q < 2; q++) s->xs[q] = s->xr[q] = s->ys[q] = s->yr[q] = nullptr;
     s->d_gather = nullptr;
     s->use_graph = getenv("SARASMG_NO_GRAPH") == nullptr;
+    s->graph_multi = getenv("SARASMG_GRAPH_MULTI") != nullptr;
     s->capturing = false; s->cap_sites = 0; s->cap_prof = nullptr; s->last_graph = nullptr;
     s->d_ipc_base = nullptr; s->ipc_base_h = 0;
     s->ipc_cta_max = getenv("SARASMG_IPC_CTA_MAX") ? atoll(getenv("SARASMG_IPC_CTA_MAX")) : 4096;
@@ -1440,6 +1456,13 @@ int sarasmg_destroy(sarasmg_handle s) {
     if (!s) return 0;
     cudaSetDevice(s->d.device);
     cudaStreamSynchronize(s->st);
+    /* graphs first: a captured NCCL collective keeps a reference on its communicator until the graph is gone */
+    for (GraphSlot *g : s->graphs) {
+        for (auto &e : g->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        cudaGraphExecDestroy(g->exec);
+        delete g;
+    }
+    s->graphs.clear();
     if (s->has_comm) ncclCommDestroy(s->comm);
     for (auto &L : s->lev) {
         for (int a = 0; a < 3; a++) cudaFree(L.buf[a]);
@@ -1449,11 +1472,6 @@ int sarasmg_destroy(sarasmg_handle s) {
     for (int q = 0; q < 3; q++) if (s->d_wall[q]) cudaFree(s->d_wall[q]);
     for (int q = 0; q < 2; q++) { cudaFree(s->xs[q]); cudaFree(s->xr[q]); cudaFree(s->ys[q]); cudaFree(s->yr[q]); }
     cudaFree(s->d_gather);
-    for (GraphSlot *g : s->graphs) {
-        for (auto &e : g->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-        cudaGraphExecDestroy(g->exec);
-        delete g;
-    }
     cudaFree(s->d_ipc_base);
     for (int q = 0; q < s->ipc_nopened; q++) cudaIpcCloseMemHandle(s->ipc_opened[q]);
     cudaFree(s->ipc_arena);
@@ -1591,11 +1609,11 @@ int sarasmg_op_update_pads(sarasmg_handle s, int which) {
     if (which < 0 || which > 2) return set_err("bad array id");
     TRY(update_pads(s, s->vLevel, s->lev[s->vLevel].buf[which]));
     CU(cudaStreamSynchronize(s->st));
-    return 0;
+    return check_ipc_error(s);
 }
-int sarasmg_op_impose_bc(sarasmg_handle s) { ENTER(s); TRY(impose_bc(s, s->vLevel)); CU(cudaStreamSynchronize(s->st)); return 0; }
-int sarasmg_op_smooth(sarasmg_handle s, int count) { ENTER(s); TRY(op_smooth(s, count)); CU(cudaStreamSynchronize(s->st)); return 0; }
-int sarasmg_op_compute_residual(sarasmg_handle s) { ENTER(s); TRY(op_compute_residual(s)); CU(cudaStreamSynchronize(s->st)); return 0; }
+int sarasmg_op_impose_bc(sarasmg_handle s) { ENTER(s); TRY(impose_bc(s, s->vLevel)); CU(cudaStreamSynchronize(s->st)); return check_ipc_error(s); }
+int sarasmg_op_smooth(sarasmg_handle s, int count) { ENTER(s); TRY(op_smooth(s, count)); CU(cudaStreamSynchronize(s->st)); return check_ipc_error(s); }
+int sarasmg_op_compute_residual(sarasmg_handle s) { ENTER(s); TRY(op_compute_residual(s)); CU(cudaStreamSynchronize(s->st)); return check_ipc_error(s); }
 int sarasmg_op_coarsen(sarasmg_handle s) { ENTER(s); TRY(op_coarsen(s)); CU(cudaStreamSynchronize(s->st)); return 0; }
 int sarasmg_op_prolong(sarasmg_handle s) { ENTER(s); TRY(op_prolong(s)); CU(cudaStreamSynchronize(s->st)); return 0; }
 int sarasmg_op_solve_coarsest(sarasmg_handle s, int *iters) { ENTER(s); return op_solve_coarsest(s, iters, true); }
