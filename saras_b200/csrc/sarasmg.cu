@@ -1110,8 +1110,8 @@ static unsigned graph_prof_key(const S *s) {
     return 1u + (unsigned)std::min(s->prof_max_level, 1000) + ((s->d.flags & SARASMG_FLAG_TIME_RUN) ? 100000u : 0u);
 }
 static int run_vcycle(S *s) {
-    /* several ranks: the graph would hold NCCL all-gathers of the agglomerated coarsest solve; replay works (2 GPUs), but
-     * tearing such a graph down next to its communicator is not validated yet, so it is opt-in (SARASMG_GRAPH_MULTI=1) */
+    /* several ranks: the graph holds the NCCL all-gathers of the agglomerated coarsest solve and must be destroyed before
+     * the communicator (sarasmg_destroy).  Bit-exact on 2 GPUs; opt-in (SARASMG_GRAPH_MULTI=1) until run on 4 and 8 */
     const bool capturable = s->use_graph && !s->gs_legacy &&
                             (s->d.n_proc == 1 || (s->graph_multi && s->agg_ok && !s->coarse_legacy));
     if (!capturable) return op_vcycle(s, nullptr);

@@ -117,13 +117,13 @@ def run_gpu(rank, world, local):
     cases.append(dict(cases[0], name=cases[0]["name"] + "_ipc_3kernel", _env="SARASMG_IPC_CTA_MAX=0"))
     cases.append(dict(cases[1], name=cases[1]["name"] + "_ipc_3kernel", _env="SARASMG_IPC_CTA_MAX=0"))
     cases.append(dict(cases[3], name=cases[3]["name"] + "_ipc_3kernel", _env="SARASMG_IPC_CTA_MAX=0"))
+    # with several ranks the CUDA-graph replay of the V-cycle (peer-memory exchanges and NCCL all-gathers inside) is opt-in
+    if os.environ.get("MP_GRAPH_CASE"):
+        cases.append(dict(cases[2], name=cases[2]["name"] + "_graph", _env="SARASMG_GRAPH_MULTI=1"))
     if os.environ.get("MP_CASES"):      # comma-separated case names (debugging on a budget)
         cases = [c for c in cases if c["name"] in os.environ["MP_CASES"].split(",")]
     if world >= 8:      # an 8-GPU box is charged eight-fold: the six core cases plus one of each variant
         cases = cases[:ncore] + [c for c in cases[ncore:] if c["name"].startswith("nnn")]
-    # with several ranks the CUDA-graph replay of the V-cycle (peer-memory exchanges and NCCL all-gathers inside) is opt-in
-    if os.environ.get("MP_GRAPH_CASE"):
-        cases.append(dict(cases[2], name=cases[2]["name"] + "_graph", _env="SARASMG_GRAPH_MULTI=1"))
     for case in cases:
         base = {k: v for k, v in case.items() if k not in ("name", "_env")}
         for key in ("SARASMG_COARSE_LEGACY", "SARASMG_HALO", "SARASMG_IPC_CTA_MAX", "SARASMG_GRAPH_MULTI"):
