@@ -20,6 +20,12 @@ CASES = [
     dict(dim=2, xInd=7, zInd=7, npX=4, vcDepth=4, vcCount=7, gsSmooth=1, resType=1),                                       # ldcTest layout
     dict(dim=2, test_poisson=1, xInd=6, zInd=6, npX=2, vcDepth=4, vcCount=10, gsSmooth=1, resType=2),
     dict(dim=2, xInd=6, zInd=5, vcDepth=3, vcCount=10, gsSmooth=0, resType=2, xPer=1, zPer=1, xGrid=2, betaX=1.2),
+    # odd number of Jacobi sweeps per cycle (the outer-array swap of d3:168 leaves the levels alternating), y-only split,
+    # resType 0 on several ranks (exactly one cycle), and the C1 grid at full depth on the shipped 2x2 layout
+    dict(dim=3, xInd=5, yInd=4, zInd=5, vcDepth=3, vcCount=9, gsSmooth=0, resType=2, mgTolerance=1e-9, preSmooth=2, postSmooth=1),
+    dict(dim=3, xInd=4, yInd=5, zInd=4, npX=1, npY=2, vcDepth=2, vcCount=8, gsSmooth=1, resType=1, zGrid=2, betaZ=1.2),
+    dict(dim=3, xInd=5, yInd=5, zInd=4, npX=2, npY=2, vcDepth=2, vcCount=7, gsSmooth=0, resType=0),
+    dict(dim=3, test_poisson=1, xInd=6, yInd=6, zInd=6, npX=2, npY=2, vcDepth=4, vcCount=6, gsSmooth=1, resType=2),
 ]
 
 
