@@ -129,6 +129,7 @@ struct sarasmg_solver_s {
     CoarseBlock *agg_tab;
     double *agg_met;            /* n_proc * 2 * ((Fx+2) + (Fy+2)) doubles: xixx, xix2, etyy, ety2 of every rank, coarsest level */
     bool agg_ok;
+    bool coarse_global;         /* SARASMG_COARSE_GLOBAL: keep the agglomerated coarsest solve in global memory (k_coarse_solve_blocks) */
     bool coarse_legacy;         /* SARASMG_COARSE_LEGACY: host-driven loop, one halo exchange + all-gather per iteration */
     /* instrumentation */
     long long launches;
@@ -997,7 +998,7 @@ static int op_solve_coarsest(S *s, int *iters, bool sync) {
         }
         const size_t smem = coarse_smem_bytes(L.v, d.dim, nblk);
         const int p2 = (divisors_pow2(s->planar, L.v.hx * L.v.hx, L.v.hx, L.v.hy, L.v.hz * L.v.hz, L.v.hz) && !s->no_pow2) ? 1 : 0;
-        if (smem <= 200 * 1024 && !getenv("SARASMG_COARSE_GLOBAL")) {
+        if (smem <= 200 * 1024 && !s->coarse_global) {
             if (s->planar) k_coarse_solve_smem<2><<<1, 256, smem, s->st>>>(Pa, Ra, (long long)L.elems, nblk, s->agg_tab, L.v, wall, m[4], m[5], p2, d.mg_tolerance, s->maxCount, s->d_iters);
             else k_coarse_solve_smem<3><<<1, 256, smem, s->st>>>(Pa, Ra, (long long)L.elems, nblk, s->agg_tab, L.v, wall, m[4], m[5], p2, d.mg_tolerance, s->maxCount, s->d_iters);
             TRY(kcheck(s, "k_coarse_solve_smem"));
@@ -1289,17 +1290,8 @@ int sarasmg_get_unique_id(void *out) {
     return 0;
 }
 
-int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
-    if (!desc || !out) return set_err("sarasmg_create: null argument");
-    if (desc->dim != 2 && desc->dim != 3) return set_err("sarasmg_create: dim must be 2 or 3");
-    if (desc->vc_depth < 0 || desc->vc_depth > 30) return set_err("sarasmg_create: bad vc_depth");
-    int ndev = 0;
-    cudaError_t ce = cudaGetDeviceCount(&ndev);
-    if (ce != cudaSuccess || ndev == 0)
-        return set_err("sarasmg_create: no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(ce));
-    CU(cudaSetDevice(desc->device));
-
-    S *s = new S();
+/* builds everything into *s; on failure the caller tears the partially built solver down */
+static int create_impl(const sarasmg_desc *desc, S *s) {
     s->d = *desc;
     s->planar = (desc->dim == 2);
     s->D = desc->vc_depth;
@@ -1331,6 +1323,7 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     for (int q = 0; q < 4; q++) { s->ipc_peer[q] = nullptr; s->ipc_opened[q] = nullptr; }
     s->agg_P = s->agg_R = nullptr; s->agg_tab = nullptr; s->agg_met = nullptr; s->agg_ok = false;
     s->coarse_legacy = getenv("SARASMG_COARSE_LEGACY") != nullptr;
+    s->coarse_global = getenv("SARASMG_COARSE_GLOBAL") != nullptr;
     CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     CU(cudaEventCreate(&s->ev_solve0));
     CU(cudaEventCreate(&s->ev_solve1));
@@ -1448,6 +1441,28 @@ int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
     s->d.xixx = s->d.xix2 = s->d.etyy = s->d.ety2 = s->d.ztzz = s->d.ztz2 = nullptr;
     s->d.x_wall = s->d.y_wall = s->d.z_wall = nullptr;
     CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+int sarasmg_create(const sarasmg_desc *desc, sarasmg_handle *out) {
+    if (!desc || !out) return set_err("sarasmg_create: null argument");
+    if (desc->dim != 2 && desc->dim != 3) return set_err("sarasmg_create: dim must be 2 or 3");
+    if (desc->vc_depth < 0 || desc->vc_depth > 30) return set_err("sarasmg_create: bad vc_depth");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return set_err("sarasmg_create: no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(ce));
+    CU(cudaSetDevice(desc->device));
+    S *s = new S();
+    const int rc = create_impl(desc, s);
+    if (rc) {                               /* free whatever was allocated; keep the message of the failure */
+        const std::string why = g_err;
+        s->d.flags &= ~SARASMG_FLAG_TIME_RUN;
+        sarasmg_destroy(s);
+        cudaGetLastError();
+        g_err = why;
+        return rc;
+    }
     *out = s;
     return 0;
 }
