@@ -37,6 +37,9 @@ struct GsPlan {
     int ntasks;
     int z_uniform;
     int tabn;               /* doubles per z table = 4 * (quads of the largest slab) */
+    int slack;              /* when the halo warp has to wait for a predecessor tile it waits until that tile is `slack` steps further
+                               than strictly needed, so that afterwards its polls succeed from the cached progress value instead of
+                               meeting every publish of the predecessor (0 = wait for exactly what is needed) */
     const int4 *tasks;      /* (I, J, Z, -) in ticket order */
     int *sync;              /* [0] ticket counter, [1 + (Z*NJ + J)*NI + I] completed steps of task (I,J,Z) */
 };
@@ -209,8 +212,8 @@ __global__ void __launch_bounds__(256, 2) k_gs_skew(double *P, const double *__r
             /* halos of consumer step c = t + GS_DH: the producers must have completed their step c + lag - 1 */
             const int c = t + GS_DH;
             if (b == 0) {
-                if (idW >= 0) seenW = gs_wait(G.sync + idW, min(c + TI, stepsW), seenW);
-                if (idL >= 0) seenL = gs_wait(G.sync + idL, min(c + GS_TJ, stepsL), seenL);
+                if (idW >= 0 && seenW < min(c + TI, stepsW)) seenW = gs_wait(G.sync + idW, min(c + TI + G.slack, stepsW), seenW);
+                if (idL >= 0 && seenL < min(c + GS_TJ, stepsL)) seenL = gs_wait(G.sync + idL, min(c + GS_TJ + G.slack, stepsL), seenL);
             }
             __syncwarp();
             {

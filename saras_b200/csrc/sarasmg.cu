@@ -569,6 +569,8 @@ static int build_gs_plan(S *s, Level &L) {
     G.ntasks = G.NI * G.NJ * G.NZ;
     G.tabn = 4 * (G.NQ - (G.NZ - 1) * G.ZQ);
     G.z_uniform = L.z_uniform ? 1 : 0;
+    G.slack = 0;
+    if (const char *e = getenv("SARASMG_GS_SLACK")) G.slack = std::max(0, atoi(e));     /* tuning knob, see GsPlan::slack */
     /* ticket order: ideal start time of a task in the systolic schedule; predecessors (I-1,J,Z), (I,J-1,Z), (I,J,Z-1) sort first */
     struct T { long long key; int I, J, Z; };
     std::vector<T> ts;
