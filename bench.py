@@ -34,6 +34,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries the one JSON line; if the environment asks NCCL for debug output (NCCL_DEBUG=VERSION prints a banner),
+# send it to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "multigrid_vcycle_glups"
 UNIT = "GLUP/s"

@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(256) k_unpack_y2(double *__restrict__ A, const
 /* the last CTA of the grid raises the remote flags; consumers read the buffers with L1-bypassing loads.     */
 /* ------------------------------------------------------------------------------------------------ */
 /* Bounded spin: a neighbour that never signals (a rank died, or ranks disagree on the exchange count) must not hang the
- * GPU.  After ~2^25 polls (seconds) the waiter records the exchange number in *err and goes on; the host turns a non-zero
+ * GPU.  After 2^27 polls (about a minute: ranks may legitimately be seconds apart) the waiter records the exchange number in *err and goes on; the host turns a non-zero
  * *err into an error at the next synchronisation point. */
 __device__ __forceinline__ void ipc_wait_flag(const unsigned *flag, const unsigned epoch, unsigned *err) {
     if (!flag) return;
@@ -823,7 +823,7 @@ __device__ __forceinline__ void ipc_wait_flag(const unsigned *flag, const unsign
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int)(v - epoch) >= 0) return;
         if ((spins & 1023u) == 1023u) __nanosleep(200);
-    } while (++spins < (1u << 25));
+    } while (++spins < (1u << 27));
     if (err) atomicMax(err, epoch | 0x80000000u);
 }
 __device__ __forceinline__ void ipc_signal(unsigned *flag, const unsigned epoch) {
