@@ -812,8 +812,8 @@ __global__ void __launch_bounds__(256) k_unpack_y2(double *__restrict__ A, const
 /* the last CTA of the grid raises the remote flags; consumers read the buffers with L1-bypassing loads.     */
 /* ------------------------------------------------------------------------------------------------ */
 /* Bounded spin: a neighbour that never signals (a rank died, or ranks disagree on the exchange count) must not hang the
- * GPU.  After 2^27 polls (about a minute: ranks may legitimately be seconds apart) the waiter records the exchange number in *err and goes on; the host turns a non-zero
- * *err into an error at the next synchronisation point. */
+ * GPU.  After 2^27 polls (about a minute: ranks may legitimately be seconds apart) the waiter records the exchange
+ * number in *err and goes on; the host turns a non-zero *err into an error at the next synchronisation point. */
 __device__ __forceinline__ void ipc_wait_flag(const unsigned *flag, const unsigned epoch, unsigned *err) {
     if (!flag) return;
     if (err && *(volatile unsigned *)err) return;          /* an earlier wait already failed: do not stack timeouts */
