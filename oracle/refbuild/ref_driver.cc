@@ -1,4 +1,10 @@
 /*
+ * Built a second time with -DSARAS_DROPIN (oracle/_ref/libsarasdropin_*.so): the SAME driver and the reference's own
+ * grid.cc / parallel.cc / parser.cc, but "poisson.h" and the solver behind it are this repository's drop-in
+ * (saras_b200/host/poisson.{h,cc} over libsarasmg.so).  That is the drop-in claim made executable: the reference's
+ * object model, unmodified, constructs `multigrid_d3 mgSolver(gridData, inputParams)` and calls
+ * `mgSolver.mgSolve(Pp, mgRHS)` exactly as hydro_d3.cc:65,343 do, and gets the CUDA solver.
+ *
  * ref_driver.cc -- runs the REFERENCE's own multigrid solver (lib/poisson/poisson*.cc, lib/grid/grid.cc,
  * lib/parallel/parallel.cc, lib/io/parser.cc compiled unmodified from /root/reference against the stand-in
  * Blitz/MPI/yaml headers of saras_b200/host/compat) and hands inputs/outputs across a C ABI so the Python
@@ -60,6 +66,8 @@ struct Job {
     double *metrics_out;      /* per rank: 6 arrays of level 0 concatenated, each F_d long; may be NULL */
     double *coef_out;         /* 9*(D+1) doubles from rank 0 (hx hy hz hx2 hz2 hzhx hxhy hyhz hxhyhz); may be NULL */
     int mode;                 /* 0 mgSolve, 1 setup only */
+    double *res_hist;         /* SARAS_DROPIN: residual history and cycle count taken from the drop-in object (rank 0) */
+    int *cycles;
 };
 
 #ifdef PLANAR
@@ -89,7 +97,11 @@ void write_yaml(const ref_params &p, const std::string &dir) {
       << "    \"Probe Time Interval\": 0.1\n    \"Probes\": >\n        [5, 5, 5]\n"
       << "\"Multigrid\":\n    \"V-Cycle Depth\": " << p.vcDepth << "\n    \"V-Cycle Count\": " << p.vcCount << "\n    \"Solve Tolerance\": " << p.mgTolerance << "\n"
       << "    \"Smoothing Method\": " << p.gsSmooth << "\n    \"Pre-Smoothing Count\": " << p.preSmooth << "\n    \"Post-Smoothing Count\": " << p.postSmooth << "\n"
+#ifdef SARAS_DROPIN
+      << "    \"Residual Type\": " << p.resType << "\n    \"Print Residual\": false\n";      /* history comes from mgSolver.lastResiduals */
+#else
       << "    \"Residual Type\": " << p.resType << "\n    \"Print Residual\": true\n";
+#endif
 }
 
 void rank_main(void *arg) {
@@ -152,6 +164,12 @@ void rank_main(void *arg) {
     memcpy(mgRHS.F.dataFirst(), job->rhs[r], n * sizeof(double));
     mgSolver.mgSolve(Pp, mgRHS);                 /* hydro_d3.cc:343 */
     memcpy(job->p_inout[r], Pp.F.dataFirst(), n * sizeof(double));
+#ifdef SARAS_DROPIN
+    if (r == 0) {
+        if (job->cycles) *job->cycles = mgSolver.lastCycles;
+        if (job->res_hist) for (int i = 0; i < mgSolver.lastCycles; i++) job->res_hist[i] = mgSolver.lastResiduals[i];
+    }
+#endif
 }
 
 }  // namespace
@@ -166,6 +184,9 @@ int sarasref_mode(void) {
 #endif
 #ifdef TEST_POISSON
     m |= 2;
+#endif
+#ifdef SARAS_DROPIN
+    m |= 4;
 #endif
     return m;
 }
@@ -185,7 +206,8 @@ int sarasref_mg_solve(const char *workdir, const ref_params *prm, double *const 
     std::streambuf *old = std::cout.rdbuf(captured.rdbuf());
     const std::streamsize oldprec = std::cout.precision(17);
 
-    Job job = {prm, p_inout, rhs, metrics_out, coef_out, mode};
+    int dropin_cycles = -1;
+    Job job = {prm, p_inout, rhs, metrics_out, coef_out, mode, res_hist, &dropin_cycles};
     saras_mpi_run(prm->npX * prm->npY, rank_main, &job);
 
     std::cout.rdbuf(old);
@@ -205,6 +227,9 @@ int sarasref_mg_solve(const char *workdir, const ref_params *prm, double *const 
             if (max_dev) *max_dev = v;
         }
     }
+#ifdef SARAS_DROPIN
+    if (mode == 0) cycles = dropin_cycles;
+#endif
     return cycles;
 }
 

@@ -19,12 +19,16 @@ REFERENCE_SRC = "/root/reference"
 _LIBS = {}
 
 
-def lib_name(dim, test_poisson, fast=False):
+def lib_name(dim, test_poisson, fast=False, dropin=False):
+    if dropin:
+        # the same driver and the reference's own grid / parallel / parser sources, with THIS repository's drop-in
+        # poisson.{h,cc} + libsarasmg.so in place of lib/poisson (oracle/refbuild/Makefile): the product under test, not an oracle
+        return "libsarasdropin_d%d%s.so" % (dim, "_test" if test_poisson else "")
     return "libsarasref_d%d%s%s.so" % (dim, "_test" if test_poisson else "", "_fast" if fast else "")
 
 
-def available(dim=3, test_poisson=0, fast=False):
-    return os.path.exists(os.path.join(REF_DIR, lib_name(dim, test_poisson, fast)))
+def available(dim=3, test_poisson=0, fast=False, dropin=False):
+    return os.path.exists(os.path.join(REF_DIR, lib_name(dim, test_poisson, fast, dropin)))
 
 
 def build():
@@ -35,8 +39,8 @@ def build():
     return True
 
 
-def _load(dim, test_poisson, fast):
-    name = lib_name(dim, test_poisson, fast)
+def _load(dim, test_poisson, fast, dropin=False):
+    name = lib_name(dim, test_poisson, fast, dropin)
     if name in _LIBS:
         return _LIBS[name]
     path = os.path.join(REF_DIR, name)
@@ -46,7 +50,7 @@ def _load(dim, test_poisson, fast):
     dp = C.POINTER(C.c_double)
     lib.sarasref_mg_solve.argtypes = [C.c_char_p, C.POINTER(MgoParams), C.POINTER(dp), C.POINTER(dp), dp, dp, dp, dp, C.c_int]
     lib.sarasref_mg_solve.restype = C.c_int
-    assert lib.sarasref_mode() == ((1 if dim == 2 else 0) | (2 if test_poisson else 0))
+    assert lib.sarasref_mode() == ((1 if dim == 2 else 0) | (2 if test_poisson else 0) | (4 if dropin else 0))
     _LIBS[name] = lib
     return lib
 
@@ -65,10 +69,11 @@ def level0_extents(cfg):
     return tuple(v + 2 for v in n)
 
 
-def mg_solve(p_list, rhs_list, fast=False, **kw):
-    """Run the reference's poisson::mgSolve on thread-ranks.  p_list[r] is overwritten.  Returns dict(cycles, residuals, max_dev)."""
+def mg_solve(p_list, rhs_list, fast=False, dropin=False, **kw):
+    """Run the reference's poisson::mgSolve on thread-ranks.  p_list[r] is overwritten.  Returns dict(cycles, residuals, max_dev).
+    dropin=True: the reference's grid / parallel / parser objects drive this repository's drop-in solver instead (needs a GPU)."""
     cfg = _cfg(kw)
-    lib = _load(cfg["dim"], cfg["test_poisson"], fast)
+    lib = _load(cfg["dim"], cfg["test_poisson"], fast, dropin)
     nr = cfg["npX"] * cfg["npY"]
     dp = C.POINTER(C.c_double)
     for a in list(p_list) + list(rhs_list):
