@@ -29,11 +29,12 @@ LAYOUTS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}
 
 def host_cases(world):
     npx, npy = LAYOUTS[world]
+    big = 5 if world <= 4 else 6        # local intervals per direction must stay >= 2^(vcDepth+1) (parser.cc:307-337)
     return [
-        dict(dim=3, xInd=5, yInd=5, zInd=4, vcDepth=2, npX=npx, npY=npy),
-        dict(dim=3, xInd=5, yInd=5, zInd=5, vcDepth=2, npX=npx, npY=npy, xPer=1, yPer=1, zPer=1, xGrid=2, zGrid=2, betaX=1.2, betaZ=1.4, wall_null=0),
-        dict(dim=3, xInd=5, yInd=5, zInd=4, vcDepth=2, npX=npx, npY=npy, test_poisson=1),
-        dict(dim=2, xInd=6, zInd=5, vcDepth=3, npX=world),
+        dict(dim=3, xInd=big, yInd=5, zInd=4, vcDepth=2, npX=npx, npY=npy),
+        dict(dim=3, xInd=big, yInd=5, zInd=5, vcDepth=2, npX=npx, npY=npy, xPer=1, yPer=1, zPer=1, xGrid=2, zGrid=2, betaX=1.2, betaZ=1.4, wall_null=0),
+        dict(dim=3, xInd=big, yInd=5, zInd=4, vcDepth=2, npX=npx, npY=npy, test_poisson=1),
+        dict(dim=2, xInd=big + 1, zInd=5, vcDepth=3, npX=world),
     ]
 
 

@@ -26,7 +26,7 @@ def _launch(mode, nproc, timeout):
     assert r.returncode == 0 and ("MP_WORKER_OK %s %d" % (mode, nproc)) in r.stdout, (r.stdout[-3000:], r.stderr[-6000:])
 
 
-@pytest.mark.parametrize("nproc", [2, 4])
+@pytest.mark.parametrize("nproc", [2, 4, 8])
 def test_host_side_process_ranks_gloo(nproc):
     _launch("host", nproc, 600)
 
