@@ -18,7 +18,12 @@ host->device and device->host copies inside the timed region.  LUP = one stencil
 coarsest level counted by its actual iteration count.
 
 The oracle (oracle/) is used here only for the cpu_baseline / --impl reference legs: oracle/_ref is the reference's own
-lib/poisson compiled unmodified with its -Ofast flags, run with one thread-rank per core.
+lib/poisson compiled unmodified with its -Ofast flags, run with one thread-rank per core.  Those legs run in a CHILD
+process (`--_cpu-leg`): the reference's fatal paths call exit(0) from inside a thread-rank (parser.cc:250-352), which no
+try/except can contain, and the GPU line must not depend on them.
+
+`config` holds only what the command line determines, so that both arms print the same object; everything measured in
+the run (cycles, residual, LUPs) is under `run`.
 """
 import argparse
 import json
@@ -42,6 +47,7 @@ METRIC = "multigrid_vcycle_glups"
 UNIT = "GLUP/s"
 LAYOUTS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}
 BYTES_PER_LUP = {"smooth": 24.0, "residual": 24.0, "coarsen": 9.0, "prolong": 17.0, "error": 16.0}
+GS_KERNEL = "k_gs_skew<3> lexicographic Gauss-Seidel"
 
 
 def parse_args():
@@ -60,7 +66,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ttt", action="store_true", help="skip the time-to-tolerance solve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-index", type=int, default=8, help="grid index of the bounded CPU sample (8 -> 257^3)")
+    ap.add_argument("--cpu-index", type=int, default=0, help="grid index of the bounded CPU sample (0: the largest of 9 / 8 that fits the time budget)")
+    ap.add_argument("--no-gs", action="store_true", help="skip the Gauss-Seidel leg (the reference YAMLs' smoother) of the default Jacobi run")
+    ap.add_argument("--_cpu-leg", dest="cpu_leg", default=None, help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -139,24 +147,36 @@ def measured_peak_hbm():
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU reference leg: oracle/_ref = the reference's own lib/poisson sources, -Ofast, thread-ranks
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_layout(cores):
-    ranks = 1
-    while ranks * 2 <= min(cores, 64):
-        ranks *= 2
-    npx = 1
-    while npx * npx < ranks:
-        npx *= 2
-    return npx, ranks // npx
+def cpu_layout(cores, index, depth):
+    """Largest power-of-two npX x npY <= cores that the reference accepts: local intervals per split direction must stay
+    >= 2^(vcDepth+1) (parser.cc:305-337, otherwise checkData prints and calls exit(0)), i.e. ranks per axis <= 2^(index-depth-1)."""
+    per_axis = max(1, 1 << max(0, index - depth - 1))
+    npx = npy = 1
+    while True:
+        if npx <= npy and npx * 2 <= per_axis and npx * 2 * npy <= min(cores, 64):
+            npx *= 2
+        elif npy * 2 <= per_axis and npx * npy * 2 <= min(cores, 64):
+            npy *= 2
+        elif npx * 2 <= per_axis and npx * 2 * npy <= min(cores, 64):
+            npx *= 2
+        else:
+            break
+    if npy > npx:
+        npx, npy = npy, npx
+    return npx, npy
 
 
-def reference_sample(a, cycles, repeats=1, warm=0):
-    """Times poisson::mgSolve of the reference on a bounded sample of the bench workload.  Returns (glups, info)."""
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def reference_solve_times(a, index, cycles, npx, npy, repeats=1, warm=0):
+    """Times poisson::mgSolve of the reference (oracle/_ref, else the oracle port) on a `index` grid.  Runs in the child."""
     from oracle import sarasref
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     kind = "reference" if sarasref.available(3, 0, fast=True) else "port"
-    index = a.cpu_index
     depth = index - 3
-    npx, npy = cpu_layout(cores) if kind == "reference" else (1, 1)
+    if kind != "reference":
+        npx, npy = 1, 1
     cfg = solver_cfg(a, index, npx, npy, depth)
     cfg["vcCount"] = cycles
     nr = npx * npy
@@ -171,6 +191,7 @@ def reference_sample(a, cycles, repeats=1, warm=0):
     n = [F[0] - 2, F[1] - 2, F[2] - 2]
     level_points = [nr * (((n[0] - 1) >> l) + 1) * (((n[1] - 1) >> l) + 1) * (((n[2] - 1) >> l) + 1) for l in range(depth + 1)]
     times = []
+    out = None
     for it in range(warm + repeats):
         P = [np.zeros(F) for _ in range(nr)]
         t0 = time.perf_counter()
@@ -184,26 +205,89 @@ def reference_sample(a, cycles, repeats=1, warm=0):
     # the reference does not report its coarsest-level iteration counts; count the coarsest level with `pre+post` sweeps
     coarse = out.get("coarse_iters", [cfg["preSmooth"] + cfg["postSmooth"]] * out["cycles"])
     lups = lups_per_solve(level_points, cfg["preSmooth"], cfg["postSmooth"], coarse)
-    sec = float(np.mean(times))
-    info = dict(kind=kind, cores=nr, host_cores=cores,
-                sample="%d^3 grid (Index %d), %d V(2,2) cycles, depth %d, %s smoother, %dx%d thread-ranks, %s" % (
-                    n[2], index, out["cycles"], depth, a.smoother, npx, npy,
-                    "reference lib/poisson compiled -Ofast (oracle/_ref)" if kind == "reference" else "oracle/mg_oracle.c -O3"),
-                seconds_per_solve=sec, lups_per_solve=lups)
-    return lups / sec / 1e9, info, times
+    sample = "%d^3 grid (Index %d), %d V(2,2) cycles per solve, depth %d, %s smoother, %dx%d thread-ranks, %s" % (
+        n[2], index, out["cycles"], depth, a.smoother, npx, npy,
+        "reference lib/poisson compiled -Ofast (oracle/_ref)" if kind == "reference" else "oracle/mg_oracle.c -O3")
+    return dict(kind=kind, cores=nr, sample=sample, times=times, lups_per_solve=lups, cycles=int(out["cycles"]))
+
+
+def cpu_leg_child(a):
+    """Child process: spec = JSON {mode, budget_s, steps, warmup}.  Prints one JSON object."""
+    spec = json.loads(a.cpu_leg)
+    cores = host_cores()
+    budget = float(spec.get("budget_s", 25.0))
+    steps, warm = int(spec.get("steps", 1)), int(spec.get("warmup", 0))
+    res = dict(host_cores=cores)
+    # probe: one cycle at 257^3 on every core the reference can use
+    npx8, npy8 = cpu_layout(cores, 8, 5)
+    probe = reference_solve_times(a, 8, 1, npx8, npy8)
+    t_cycle8 = probe["times"][0]
+    res["probe"] = dict(sample=probe["sample"], seconds=t_cycle8)
+    # choose the sample: 513^3 (the largest grid the CPU arm can afford) if `steps + warmup` solves of >= 2 cycles fit the budget
+    index = a.cpu_index
+    if index == 0:
+        npx9, npy9 = cpu_layout(cores, 9, 6)
+        t_cycle9 = t_cycle8 * 8.0 * (npx8 * npy8) / (npx9 * npy9)
+        index = 9 if (steps + warm) * 2 * t_cycle9 <= budget else 8
+    depth = index - 3
+    npx, npy = cpu_layout(cores, index, depth)
+    t_cycle = t_cycle8 * (8.0 ** (index - 8)) * (npx8 * npy8) / (npx * npy)
+    cycles = int(max(1, min(a.cycles, budget / max((steps + warm) * t_cycle, 1e-6))))
+    r = reference_solve_times(a, index, cycles, npx, npy, repeats=steps, warm=warm)
+    sec = float(np.mean(r["times"]))
+    res.update(kind=r["kind"], cores=r["cores"], sample=r["sample"], seconds_per_solve=sec, times=r["times"],
+               value=r["lups_per_solve"] / sec / 1e9, lups_per_solve=r["lups_per_solve"], layout=[npx, npy], index=index)
+    if spec.get("single_core", False):
+        # np = 1 on one core: 2 cycles at 257^3 (about 3 s)
+        r1 = reference_solve_times(a, 8, 2, 1, 1)
+        res["single_core"] = dict(value=r1["lups_per_solve"] / r1["times"][0] / 1e9, unit=UNIT, cores=1, sample=r1["sample"], seconds=r1["times"][0])
+    print("CPU_LEG_JSON " + json.dumps(res), flush=True)
+
+
+def run_cpu_leg(a, spec, timeout):
+    """Runs the CPU leg in a child process and returns its result dict (or a dict with kind == 'unavailable')."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--_cpu-leg", json.dumps(spec),
+           "--index", str(a.index), "--cycles", str(a.cycles), "--smoother", a.smoother, "--mesh", a.mesh,
+           "--tolerance", repr(a.tolerance), "--cpu-index", str(a.cpu_index)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return dict(kind="unavailable", why="CPU leg exceeded %d s" % timeout)
+    for line in r.stdout.splitlines():
+        if line.startswith("CPU_LEG_JSON "):
+            return json.loads(line[len("CPU_LEG_JSON "):])
+    return dict(kind="unavailable", why="CPU leg ended with rc %d and no result: %s" % (r.returncode, (r.stderr or r.stdout)[-300:].replace("\n", " | ")))
+
+
+def bench_config(a, npx, npy, level0_bytes=None):
+    """what the command line determines -- identical in both arms"""
+    n = (1 << a.index) + 1
+    if level0_bytes is None:
+        level0_bytes = ((n - 1) // npx + 3) * ((n - 1) // npy + 3) * (n + 2) * 8
+    return dict(workload=workload_name(a, npx, npy),
+                l2="inputs larger than L2 (level-0 arrays %.2f GB each per GPU vs 126 MB L2)" % (level0_bytes / 1e9),
+                cycles_per_solve_max=a.cycles, tolerance=a.tolerance)
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    glups, info, times = reference_sample(a, a.cycles, repeats=a.steps, warm=a.warmup)
-    ms = 1e3 * float(np.mean(times))
     npx, npy = LAYOUTS.get(a.gpus, (1, 1))
-    line = dict(metric=METRIC, value=glups, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=ms,
+    res = run_cpu_leg(a, dict(steps=a.steps, warmup=a.warmup, budget_s=120.0), timeout=900)
+    if res.get("kind") == "unavailable":
+        # last resort: one rank at 257^3 (always a valid layout)
+        a.cpu_index = 8
+        res = run_cpu_leg(a, dict(steps=a.steps, warmup=a.warmup, budget_s=60.0), timeout=600)
+    if res.get("kind") == "unavailable":
+        print(json.dumps(dict(impl="reference", unavailable=res.get("why", "CPU leg failed"))), flush=True)
+        return
+    glups = res["value"]
+    line = dict(metric=METRIC, value=glups, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=1e3 * res["seconds_per_solve"],
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=workload_name(a, npx, npy), sample=info["sample"]),
-                cpu_baseline=dict(value=glups, unit=UNIT, cores=info["cores"], kind=info["kind"], sample=info["sample"]),
+                config=bench_config(a, npx, npy),
+                cpu_baseline=dict(value=glups, unit=UNIT, cores=res["cores"], kind=res["kind"], sample=res["sample"], host_cores=res["host_cores"]),
                 e2e=dict(value=glups, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
 
@@ -299,31 +383,41 @@ def run_b200(a):
     lups_step = lups_per_solve(level_points, pre, post, outs[-1]["coarse_iters"])
     value = lups_step * a.steps / (ms_total * 1e-3) / 1e9
 
-    # per-operator device times of the fine levels, measured live with CUDA events over the timed region
+    # per-operator device times of the fine levels, measured live with CUDA events over the timed region (the event pairs of
+    # levels <= 1 are recorded INSIDE the timed region: ~60 records per cycle, no synchronisation)
     peak, peak_src = measured_peak_hbm()
-    per_level = []
-    for lvl in range(min(2, depth + 1)):
-        for kind, name in ((capi.K_SMOOTH, "smooth"), (capi.K_RESIDUAL, "residual"), (capi.K_COARSEN, "coarsen"),
-                           (capi.K_PROLONG, "prolong"), (capi.K_ERROR, "error")):
-            ms, n = s.profile_query(kind, lvl)
-            if n == 0:
-                continue
-            pts = level_points_local[lvl]
-            gbs = BYTES_PER_LUP[name] * pts / (ms / n * 1e-3) / 1e9
-            per_level.append(dict(level=lvl, op=name, launches=int(n), avg_ms=ms / n, gbs=gbs, frac=gbs / peak))
-    dom = next((e for e in per_level if e["level"] == 0 and e["op"] == "smooth"), None)
-    roofline = None
-    if dom:
+
+    def fine_level_table():
+        rows = []
+        for lvl in range(min(2, depth + 1)):
+            for kind, name in ((capi.K_SMOOTH, "smooth"), (capi.K_RESIDUAL, "residual"), (capi.K_COARSEN, "coarsen"),
+                               (capi.K_PROLONG, "prolong"), (capi.K_ERROR, "error")):
+                ms, n = s.profile_query(kind, lvl)
+                if n == 0:
+                    continue
+                pts = level_points_local[lvl]
+                gbs = BYTES_PER_LUP[name] * pts / (ms / n * 1e-3) / 1e9
+                rows.append(dict(level=lvl, op=name, launches=int(n), avg_ms=ms / n, gbs=gbs, frac=gbs / peak))
+        return rows
+
+    def roofline_of(rows, smoother):
+        dom = next((e for e in rows if e["level"] == 0 and e["op"] == "smooth"), None)
+        if not dom:
+            return None
         traffic = None      # DRAM bytes per launch of this kernel from the committed ncu capture (same grid, same layout only)
         if a.gpus == 1 and a.index == 10 and a.mesh == "uniform":
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_1025_n1.json")))[a.smoother]["bytes"]
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_1025_n1.json")))[smoother]["bytes"]
             except Exception:
                 traffic = None
-        roofline = dict(bound="hbm", achieved=dom["gbs"], peak=peak, unit="GB/s", frac=dom["gbs"] / peak, traffic=traffic,
-                        kernel="level-0 smoother sweep (%s)" % ("k_gs_skew<3> lexicographic Gauss-Seidel" if a.smoother == "gs" else "k_stencil_tma<0> Jacobi, TMA-staged x-march"),
-                        algorithmic_bytes_per_launch=BYTES_PER_LUP["smooth"] * level_points_local[0], avg_launch_ms=dom["avg_ms"],
-                        peak_source=peak_src)
+        return dict(bound="hbm", achieved=dom["gbs"], peak=peak, unit="GB/s", frac=dom["gbs"] / peak, traffic=traffic,
+                    traffic_source="profiles/traffic_1025_n1.json (ncu --set full capture of this kernel, 1 GPU, 1025^3 uniform); null for other layouts",
+                    kernel="level-0 smoother sweep (%s)" % (GS_KERNEL if smoother == "gs" else "k_stencil_tma<0> Jacobi, TMA-staged x-march"),
+                    algorithmic_bytes_per_launch=BYTES_PER_LUP["smooth"] * level_points_local[0], avg_launch_ms=dom["avg_ms"],
+                    peak_source=peak_src)
+
+    per_level = fine_level_table()
+    roofline = roofline_of(per_level, a.smoother)
 
     breakdown = None
     if a.breakdown:
@@ -363,8 +457,7 @@ def run_b200(a):
     s.set_profile_max_level(1)
 
     # time to tolerance: the same hierarchy run until the reference's stagnation test |r_prev - r| < mgTolerance stops it
-    ttt = None
-    if not a.no_ttt:
+    def time_to_tolerance():
         s.set_vc_count(60)
         s.reset_counters()
         barrier(); s.synchronize()
@@ -372,9 +465,37 @@ def run_b200(a):
         out_t = s.solve_resident()
         s.event_record(3)
         ms_t = allmax(s.event_elapsed_ms(2, 3))
-        ttt = dict(ms=ms_t, cycles=int(out_t["cycles"]), tolerance=a.tolerance, final_residual=float(out_t["residuals"][-1]),
-                   rule="poisson.cc:145 stagnation test, at most 60 cycles")
         s.set_vc_count(a.cycles)
+        return dict(ms=ms_t, cycles=int(out_t["cycles"]), tolerance=a.tolerance, final_residual=float(out_t["residuals"][-1]),
+                    stagnated=bool(out_t["cycles"] < 60), rule="poisson.cc:145 stagnation test, at most 60 cycles")
+
+    ttt = None
+    if not a.no_ttt:
+        ttt = {a.smoother: time_to_tolerance()}
+
+    # the reference YAMLs' smoother on the same resident hierarchy: lexicographic Gauss-Seidel (Smoothing Method: 1 in input/,
+    # tests/mgTest, tests/ldcTest).  Same problem, same timing rules; reported beside the Jacobi headline.
+    gs = None
+    if a.smoother == "jacobi" and not a.no_gs:
+        s.set_smoother(1)
+        for _ in range(2):
+            out_g = s.solve_resident()
+        s.reset_counters()
+        barrier(); s.synchronize()
+        gsteps = max(2, min(a.steps, 5))
+        s.event_record(4)
+        for _ in range(gsteps):
+            out_g = s.solve_resident()
+        s.event_record(5)
+        ms_g = allmax(s.event_elapsed_ms(4, 5))
+        lups_g = lups_per_solve(level_points, pre, post, out_g["coarse_iters"])
+        rows_g = fine_level_table()
+        gs = dict(value=lups_g * gsteps / (ms_g * 1e-3) / 1e9, unit=UNIT, steps=gsteps, ms_per_step=ms_g / gsteps,
+                  cycles_per_step=int(out_g["cycles"]), final_residual=float(out_g["residuals"][-1]),
+                  roofline=roofline_of(rows_g, "gs"), per_level=rows_g)
+        if not a.no_ttt:
+            ttt["gs"] = time_to_tolerance()
+        s.set_smoother(0)
 
     # ---- end-to-end arm: mgSolver.mgSolve(Pp, mgRHS) on host plainsf arrays ---------------------------------------
     e2e = None
@@ -392,28 +513,25 @@ def run_b200(a):
         e2e = dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(allsum(2 * nbytes)), d2h_bytes_per_step=int(allsum(nbytes)),
                    ms_per_step=1e3 * float(np.mean(e2e_times)), api="multigrid_d3::mgSolve(plainsf&, const plainsf&) on host arrays (C++ drop-in over the C-ABI)")
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------------
+    # ---- CPU baseline beside it (rank 0, N = 1 only), in a child process --------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        try:
-            g1, info1, t1 = reference_sample(a, 2)
-            cyc = int(min(40, max(2, math.ceil(12.0 / max(t1[0] / 2.0, 1e-3)))))
-            g, info, _ = reference_sample(a, cyc)
-            cpu = dict(value=g, unit=UNIT, cores=info["cores"], kind=info["kind"], sample=info["sample"],
-                       seconds=info["seconds_per_solve"], host_cores=info["host_cores"])
-        except Exception as e:  # the baseline is a reported number, never a dependency of the GPU arm
-            cpu = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=str(e))
+        r = run_cpu_leg(a, dict(steps=1, warmup=0, budget_s=20.0, single_core=True), timeout=600)
+        if r.get("kind") == "unavailable":
+            cpu = dict(value=None, unit=UNIT, cores=0, kind="unavailable", sample=r.get("why", ""))
+        else:
+            cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"],
+                       seconds=r["seconds_per_solve"], host_cores=r["host_cores"], single_core=r.get("single_core"))
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                     ms_per_step=ms_total / a.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
-                    data="synthetic",
-                    config=dict(workload=workload_name(a, npx, npy), l2="inputs larger than L2 (level-0 arrays %.2f GB each per GPU vs 126 MB L2)" % (nbytes / 1e9),
-                                cycles_per_step=int(outs[-1]["cycles"]), final_residual=float(outs[-1]["residuals"][-1]),
-                                coarse_iters=[int(v) for v in outs[-1]["coarse_iters"]], lups_per_step=lups_step,
-                                fine_point_vcycles_per_s=level_points[0] * outs[-1]["cycles"] * a.steps / (ms_total * 1e-3)),
+                    data="synthetic", config=bench_config(a, npx, npy, nbytes),
+                    run=dict(cycles_per_step=int(outs[-1]["cycles"]), final_residual=float(outs[-1]["residuals"][-1]),
+                             coarse_iters=[int(v) for v in outs[-1]["coarse_iters"]], lups_per_step=lups_step,
+                             fine_point_vcycles_per_s=level_points[0] * outs[-1]["cycles"] * a.steps / (ms_total * 1e-3)),
                     clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, per_level=per_level, per_level_all=per_level_all,
-                    time_to_tolerance=ttt, cpu_baseline=cpu, breakdown=breakdown)
+                    gauss_seidel=gs, time_to_tolerance=ttt, cpu_baseline=cpu, breakdown=breakdown)
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:
@@ -422,7 +540,9 @@ def run_b200(a):
 
 def main():
     a = parse_args()
-    if a.impl == "reference":
+    if a.cpu_leg:
+        cpu_leg_child(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)

@@ -151,17 +151,28 @@ int sarasmg_set_profile_max_level(sarasmg_handle h, int max_level);
 int sarasmg_event_record(sarasmg_handle h, int slot);
 int sarasmg_event_elapsed_ms(sarasmg_handle h, int slot_a, int slot_b, double *ms);
 /* page-lock a caller-owned host range (the Blitz storage of Pp / mgRHS, which SARAS allocates once and reuses every
- * time step) so that the copies of sarasmg_solve run at PCIe speed.  sarasmg_solve does this by itself the first time it
- * sees a pointer unless SARASMG_NO_PIN is set in the environment; ranges are released by sarasmg_destroy. */
+ * time step) so that the copies of sarasmg_solve run at PCIe speed.  Nothing is ever pinned implicitly: the library cannot
+ * know the lifetime of a caller's buffer.  LIFETIME: the range must stay allocated until sarasmg_host_unregister(ptr) or
+ * sarasmg_destroy(h) -- freeing registered memory is undefined behaviour (CUDA).  The C++ drop-in registers the contiguous
+ * storage of the plainsf objects it is handed (never its own temporary staging copies) and unregisters them in ~poisson,
+ * which runs before the fields die in every SARAS solver (hydro.h: Pp / mgRHS are base-class members, mgSolver a
+ * derived-class member). */
 int sarasmg_host_register(sarasmg_handle h, const void *ptr, unsigned long long bytes);
-/* TEST HOOK.  mgSolve subtracts globalAvg = mean of the padded RHS (poisson.cc:122-128).  The reference forms that mean
- * with one sequential sum whose rounding error (~1e-14 relative) no parallel reduction reproduces, and the singular
- * Neumann/periodic solve amplifies it ~100x.  With enable != 0 the solver subtracts `value` instead, so a test can feed
- * the oracle's mean and then require bit-exact fields in production mode as well. */
+int sarasmg_host_unregister(sarasmg_handle h, const void *ptr);
+/* mgSolve subtracts globalAvg = mean of the padded RHS (poisson.cc:122-128).  The reference forms that mean with ONE
+ * sequential fp64 sum, whose rounding error (~sqrt(n) ulp of the sum) depends on the traversal order of blitz::mean and is
+ * not reproduced by any parallel reduction; the singular Neumann / periodic solve amplifies it ~100x in the field.  The
+ * device forms the CORRECTLY ROUNDED sum (compensated summation), i.e. the value the reference's sum approximates.
+ * TEST HOOK: with enable != 0 the solver subtracts `value` instead, so a test can feed the oracle's mean and then require
+ * bit-exact fields in production mode as well.  sarasmg_last_rhs_mean returns the globalAvg of the last solve. */
 int sarasmg_debug_set_rhs_mean(sarasmg_handle h, int enable, double value);
+int sarasmg_last_rhs_mean(sarasmg_handle h, double *value);
 /* parser::vcCount of the handle (the reference reads it once from the YAML; a benchmark uses this to run the same hierarchy
  * to stagnation for the time-to-tolerance figure).  History buffers passed to the solve calls must hold `count` entries. */
 int sarasmg_set_vc_count(sarasmg_handle h, int count);
+/* parser::gsSmooth of the handle (0 Jacobi, 1 lexicographic Gauss-Seidel): lets a benchmark time both smoothers on one
+ * resident hierarchy.  Takes effect at the next solve / operator call. */
+int sarasmg_set_smoother(sarasmg_handle h, int gs_smooth);
 /* blocks until all work of the handle has finished */
 int sarasmg_synchronize(sarasmg_handle h);
 

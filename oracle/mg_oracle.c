@@ -44,6 +44,7 @@ struct mgo_solver {
     rank_state *rk;
     double lups;
     double lastGlobalAvg;
+    int exactMean;              /* test mode: local sums of the RHS mean are correctly rounded (exact_sum) instead of sequential */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -326,6 +327,53 @@ int mgo_get_level(const mgo_solver *s) { return s->vLevel; }
 void mgo_set_zero_bc(mgo_solver *s, int z) { s->zeroBC = z; }
 double mgo_lup_count(const mgo_solver *s) { return s->lups; }
 double mgo_last_global_avg(const mgo_solver *s) { return s->lastGlobalAvg; }
+void mgo_set_exact_mean(mgo_solver *s, int on) { s->exactMean = on; }
+
+/* Correctly rounded sum of n doubles (Shewchuk's non-overlapping partials, the algorithm behind Python's math.fsum).
+ * NOT the reference's arithmetic: poisson.cc:122 is one running fp64 sum.  It exists so that a test can show that the
+ * device's compensated sum is the exact mean, i.e. that the production-mode field difference between the CUDA path and the
+ * reference is the rounding error of the REFERENCE's sequential sum and nothing else (tests/test_gpu_parity.py). */
+static double exact_sum(const double *a, size_t n) {
+    double part[64];
+    int np = 0;
+    for (size_t q = 0; q < n; q++) {
+        double x = a[q];
+        int i = 0;
+        for (int j = 0; j < np; j++) {
+            double y = part[j];
+            if (fabs(x) < fabs(y)) { const double t = x; x = y; y = t; }
+            const double hi = x + y;
+            const double lo = y - (hi - x);
+            if (lo != 0.0) part[i++] = lo;
+            x = hi;
+        }
+        np = i;
+        if (np >= 63) {                                     /* cannot happen for finite doubles (<= 40 partials); stay safe */
+            double t = x;
+            for (int j = 0; j < np; j++) t += part[j];
+            x = t; np = 0;
+        }
+        part[np++] = x;
+    }
+    double hi = 0.0, lo = 0.0;
+    int m = np;
+    if (m > 0) {
+        hi = part[--m];
+        while (m > 0) {
+            const double x = hi, y = part[--m];
+            hi = x + y;
+            const double yr = hi - x;
+            lo = y - yr;
+            if (lo != 0.0) break;
+        }
+        /* round-half-even correction when the discarded tail points the same way as lo */
+        if (m > 0 && ((lo < 0.0 && part[m - 1] < 0.0) || (lo > 0.0 && part[m - 1] > 0.0))) {
+            const double y = lo * 2.0, x = hi + y, yr = x - hi;
+            if (y == yr) hi = x;
+        }
+    }
+    return hi;
+}
 void mgo_lup_reset(mgo_solver *s) { s->lups = 0.0; }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -919,7 +967,8 @@ int mgo_mg_solve(mgo_solver *s, double *const *p_inout, const double *const *rhs
         for (int r = 0; r < s->nProc; r++) {
             const double *Rh = s->rk[r].arr[MGO_RESIDUAL][0];
             double sum = 0.0;                               /* blitz::mean: sequential sum in storage order / count */
-            for (size_t q = 0; q < L0->size; q++) sum += Rh[q];
+            if (s->exactMean) sum = exact_sum(Rh, L0->size);
+            else for (size_t q = 0; q < L0->size; q++) sum += Rh[q];
             double localMean = sum / (double)L0->size;
             globalAvg += localMean;                         /* MPI_SUM in rank order */
         }
@@ -1004,5 +1053,4 @@ double mgo_test_prolong(mgo_solver *s) {
     return worst;
 }
 
-double mgo_test_transfer(mgo_solver *s) { (void)s; return 0.0; }
-double mgo_test_periodic(mgo_solver *s) { (void)s; return 0.0; }
+

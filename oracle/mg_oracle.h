@@ -98,16 +98,19 @@ void mgo_vcycle(mgo_solver *s);
 int mgo_mg_solve(mgo_solver *s, double *const *p_inout, const double *const *rhs,
                  double *res_hist, int *coarse_iters, double *max_dev);
 
-/* self tests of the reference (poisson_d3.cc:689-857, poisson_d2.cc:481-602); max over ranks */
+/* testProlong of the reference (poisson_d3.cc:689-719, poisson_d2.cc:481-507); max over ranks.  testTransfer and
+ * testPeriodic (d3:722-857) have no oracle twin: their expected values are analytic (the neighbour's index pattern, the
+ * periodic continuation of sin*cos*cos) and the GPU self tests compare against those directly. */
 double mgo_test_prolong(mgo_solver *s);
-double mgo_test_transfer(mgo_solver *s);
-double mgo_test_periodic(mgo_solver *s);
 
 /* LUP counters since creation/reset: smoother + residual + error-norm stencil evaluations */
 double mgo_lup_count(const mgo_solver *s);
 void mgo_lup_reset(mgo_solver *s);
 /* globalAvg subtracted from the RHS by the last mgo_mg_solve (poisson.cc:122-128) */
 double mgo_last_global_avg(const mgo_solver *s);
+/* TEST MODE, not the reference's arithmetic: form the local sums of that mean correctly rounded (exact summation)
+ * instead of with the reference's one sequential fp64 sum; see exact_sum in mg_oracle.c */
+void mgo_set_exact_mean(mgo_solver *s, int on);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,7 @@ def _load(fast=False):
     lib.mgo_lup_count.restype = C.c_double
     lib.mgo_last_global_avg.restype = C.c_double
     lib.mgo_last_global_avg.argtypes = [vp]
+    lib.mgo_set_exact_mean.argtypes = [vp, C.c_int]
     lib.mgo_lup_count.argtypes = [vp]
     _LIBS[key] = lib
     return lib
@@ -217,6 +218,10 @@ class Oracle:
 
     def lups(self):
         return self.lib.mgo_lup_count(self.h)
+
+    def set_exact_mean(self, on=True):
+        """TEST MODE (not the reference's arithmetic): correctly rounded local sums in the RHS mean of mg_solve"""
+        self.lib.mgo_set_exact_mean(self.h, int(on))
 
     def last_global_avg(self):
         return self.lib.mgo_last_global_avg(self.h)

@@ -51,7 +51,7 @@ SYMBOLS = [
     "sarasmg_timers", "sarasmg_kernel_launches", "sarasmg_reset_counters", "sarasmg_profile_query",
     "sarasmg_last_solve_ms", "sarasmg_synchronize", "sarasmg_debug_set_rhs_mean",
     "sarasmg_set_profile_max_level", "sarasmg_event_record", "sarasmg_event_elapsed_ms", "sarasmg_host_register",
-    "sarasmg_set_vc_count",
+    "sarasmg_set_vc_count", "sarasmg_host_unregister", "sarasmg_set_smoother", "sarasmg_last_rhs_mean",
 ]
 
 
@@ -102,6 +102,9 @@ def load():
     lib.sarasmg_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, _dp]
     lib.sarasmg_host_register.argtypes = [vp, C.c_void_p, C.c_ulonglong]
     lib.sarasmg_set_vc_count.argtypes = [vp, C.c_int]
+    lib.sarasmg_host_unregister.argtypes = [vp, C.c_void_p]
+    lib.sarasmg_set_smoother.argtypes = [vp, C.c_int]
+    lib.sarasmg_last_rhs_mean.argtypes = [vp, _dp]
     _lib = lib
     return lib
 
@@ -334,6 +337,11 @@ class Solver:
     def debug_set_rhs_mean(self, enable, value=0.0):
         self._check(self.lib.sarasmg_debug_set_rhs_mean(self.h, int(enable), float(value)))
 
+    def last_rhs_mean(self):
+        v = C.c_double(0.0)
+        self._check(self.lib.sarasmg_last_rhs_mean(self.h, C.byref(v)))
+        return v.value
+
     def set_vc_count(self, count):
         self._check(self.lib.sarasmg_set_vc_count(self.h, int(count)))
         self.vc_count = max(int(count), 1)
@@ -353,7 +361,14 @@ class Solver:
         return v.value
 
     def host_register(self, arr):
+        """page-lock `arr` for this handle; the caller keeps it alive until host_unregister / close"""
         self._check(self.lib.sarasmg_host_register(self.h, C.c_void_p(arr.ctypes.data), arr.nbytes))
+
+    def host_unregister(self, arr):
+        self._check(self.lib.sarasmg_host_unregister(self.h, C.c_void_p(arr.ctypes.data)))
+
+    def set_smoother(self, gs):
+        self._check(self.lib.sarasmg_set_smoother(self.h, int(gs)))
 
 
 def get_unique_id():

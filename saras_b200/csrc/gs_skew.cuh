@@ -83,7 +83,9 @@ __device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gp
 __device__ __forceinline__ int gs_wait(const int *p, const int need, int seen) {
     if (seen >= need) return seen;
     while ((seen = ld_relaxed(p)) < need) __nanosleep(20);
-    return seen;                                        /* the halo data itself is read with L2-coherent (.cg) loads issued after this */
+    fence_acq_rel();                                    /* acquire: orders the halo loads issued after this (by this lane and, after __syncwarp, by
+                                                           the other lanes) behind the producer's st.release of the progress word */
+    return seen;
 }
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

@@ -343,6 +343,53 @@ __device__ __forceinline__ double block_reduce(double v, double *sm /* >= 32 dou
     return v;
 }
 
+/* Compensated (cascaded) summation for the RHS mean of mgSolve (p:122): the running sum s carries the rounding error of
+ * every addition in c (Knuth two-sum; exact under -fmad=false), so s + c is the exact sum to ~2^-100 and its rounding is the
+ * correctly rounded sum whatever the reduction tree.  The reference's own value is ONE sequential fp64 sum whose rounding
+ * (~sqrt(n) ulp) no parallel order reproduces; the device value is the exact mean instead. */
+struct csum { double s, c; };
+__device__ __forceinline__ void cs_add(csum &a, const double x) {
+    const double t = a.s + x;
+    const double bb = t - a.s;
+    a.c += (a.s - (t - bb)) + (x - bb);
+    a.s = t;
+}
+__device__ __forceinline__ void cs_merge(csum &a, const double s2, const double c2) {
+    cs_add(a, s2);
+    a.c += c2;
+}
+/* deterministic block reduction of a compensated sum; result valid in thread 0; sm >= 64 doubles */
+__device__ __forceinline__ csum block_reduce_cs(csum v, double *sm) {
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int nthr = blockDim.x * blockDim.y;
+    const int lane = tid & 31, w = tid >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        const double s2 = __shfl_down_sync(0xffffffffu, v.s, o), c2 = __shfl_down_sync(0xffffffffu, v.c, o);
+        cs_merge(v, s2, c2);
+    }
+    __syncthreads();
+    if (lane == 0) { sm[2 * w] = v.s; sm[2 * w + 1] = v.c; }
+    __syncthreads();
+    const int nw = (nthr + 31) >> 5;
+    if (w == 0) {
+        v.s = (lane < nw) ? sm[2 * lane] : 0.0;
+        v.c = (lane < nw) ? sm[2 * lane + 1] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            const double s2 = __shfl_down_sync(0xffffffffu, v.s, o), c2 = __shfl_down_sync(0xffffffffu, v.c, o);
+            cs_merge(v, s2, c2);
+        }
+    }
+    return v;
+}
+/* final stage for compensated partials: part[2b], part[2b+1] = (s, c) of block b; out[0] = fl(s + c) of the total */
+__global__ void __launch_bounds__(1024) k_reduce_final_cs(const double *__restrict__ part, const int n, double *__restrict__ out) {
+    __shared__ double sm[64];
+    csum v = {0.0, 0.0};
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) cs_merge(v, part[2 * idx], part[2 * idx + 1]);
+    v = block_reduce_cs(v, sm);
+    if (threadIdx.x == 0) out[0] = v.s + v.c;
+}
+
 template <int DIM, bool P2>
 __global__ void __launch_bounds__(256, MG_ERROR_MINB)
 k_error_march(const double *__restrict__ P, const double *__restrict__ R, const LevelView L, const int ichunk,
@@ -463,10 +510,10 @@ __global__ void __launch_bounds__(256) k_sub_scalar_padded(double *__restrict__ 
 __global__ void __launch_bounds__(256) k_load_inputs(const double *__restrict__ inP, const double *__restrict__ inR,
                                                      double *__restrict__ P, double *__restrict__ R, const LevelView L,
                                                      double *__restrict__ part) {
-    __shared__ double sm[32];
+    __shared__ double sm[64];
     const long long rows = (long long)L.Fx * L.Fy;
     const int npair = L.pitch / 2;
-    double acc = 0.0;
+    csum acc = {0.0, 0.0};
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const int i = (int)(row / L.Fy) - 1, j = (int)(row % L.Fy) - 1;
         const bool core_row = (i >= 0 && i < L.nx && j >= 0 && j < L.ny);
@@ -476,25 +523,25 @@ __global__ void __launch_bounds__(256) k_load_inputs(const double *__restrict__ 
             double2 p = make_double2(0.0, 0.0), r = make_double2(0.0, 0.0);
             if (core_row && k + 1 >= 0 && k < L.nz) {
                 const double2 a = ld2(inP + base + 2 * q), b = ld2(inR + base + 2 * q);
-                if (k >= 0) { p.x = a.x; r.x = b.x; acc += b.x; }
-                if (k + 1 < L.nz) { p.y = a.y; r.y = b.y; acc += b.y; }
+                if (k >= 0) { p.x = a.x; r.x = b.x; cs_add(acc, b.x); }
+                if (k + 1 < L.nz) { p.y = a.y; r.y = b.y; cs_add(acc, b.y); }
             }
             st2(P + base + 2 * q, p);
             st2(R + base + 2 * q, r);
         }
     }
-    acc = block_reduce<false>(acc, sm);
-    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    acc = block_reduce_cs(acc, sm);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = acc.s; part[2 * blockIdx.x + 1] = acc.c; }
 }
 
 /* sum over the pad shell of a level array: x-pad planes, y-pad rows of the core planes, z-pad ends of the core rows */
 __global__ void __launch_bounds__(256) k_reduce_shell(const double *__restrict__ A, const LevelView L, double *__restrict__ part) {
-    __shared__ double sm[32];
+    __shared__ double sm[64];
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
     const long long nXp = 2LL * L.Fy * L.Fz;                    /* planes i = -1, nx: every (j, k) */
     const long long nYp = 2LL * L.nx * L.Fz;                    /* rows j = -1, ny of the core planes: every k */
     const long long nZp = 2LL * L.nx * L.ny;                    /* k = -1, nz of the core rows */
-    double acc = 0.0;
+    csum acc = {0.0, 0.0};
     for (long long q = tid; q < nXp + nYp + nZp; q += nthr) {
         int i, j, k;
         if (q < nXp) {
@@ -507,10 +554,10 @@ __global__ void __launch_bounds__(256) k_reduce_shell(const double *__restrict__
             const long long w = q - nXp - nYp, h = (long long)L.nx * L.ny;
             k = (w < h) ? -1 : L.nz; i = (int)((w % h) / L.ny); j = (int)(w % L.ny);
         }
-        acc += A[mg_at(L, i, j, k)];
+        cs_add(acc, A[mg_at(L, i, j, k)]);
     }
-    acc = block_reduce<false>(acc, sm);
-    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    acc = block_reduce_cs(acc, sm);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = acc.s; part[2 * blockIdx.x + 1] = acc.c; }
 }
 
 __global__ void __launch_bounds__(256) k_sub_rows(double *__restrict__ A, const LevelView L, const double v) {

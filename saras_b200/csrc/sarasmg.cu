@@ -144,6 +144,7 @@ struct sarasmg_solver_s {
     int last_coarse_iters;
     int mean_override;          /* test hook: use mean_value instead of the device-computed RHS mean */
     double mean_value;
+    double last_mean;           /* globalAvg subtracted by the last solve */
     int prof_max_level;         /* events only for operators on levels <= this */
     bool coarsen_legacy;        /* SARASMG_COARSEN_LEGACY: thread-per-coarse-point restriction kernel */
     bool prolong_legacy;        /* SARASMG_PROLONG_LEGACY: thread-per-fine-point prolongation kernel */
@@ -972,6 +973,17 @@ static int setup_agglomeration(S *s) {
     return 0;
 }
 
+/* The single-CTA coarsest solve replays every rank block and runs the whole while(true) in one kernel: right for the few
+ * hundred points a sensible vcDepth leaves, an unbounded single-kernel runtime for a shallow hierarchy (a 65^3 coarsest
+ * level would keep one SM busy for up to maxCount ~ 3e5 sweeps).  Above this many points (all rank blocks together) the
+ * host-driven loop with the multi-CTA sweep is used instead; it is not graph-capturable. */
+static bool coarse_in_one_cta(const S *s) {
+    const LevelView &v = s->lev[s->D].v;
+    long long lim = 40000;
+    if (const char *e = getenv("SARASMG_COARSE_CTA_MAX")) lim = atoll(e);
+    return (long long)s->d.n_proc * v.nx * v.ny * v.nz <= lim;
+}
+
 /* solve (d3:190-247, d2:150-199) */
 static int op_solve_coarsest(S *s, int *iters, bool sync) {
     const int l = s->vLevel;
@@ -981,7 +993,8 @@ static int op_solve_coarsest(S *s, int *iters, bool sync) {
     bool remote = false;
     for (int f = 0; f < 4; f++) if (fr[f] != SARASMG_PROC_NULL && fr[f] != d.rank) remote = true;
     ProfScope ps(s, SARASMG_K_COARSE_SOLVE, l);
-    if (s->agg_ok && !s->coarse_legacy && l == s->D) {
+    const bool one_cta = coarse_in_one_cta(s);
+    if (s->agg_ok && !s->coarse_legacy && l == s->D && one_cta) {
         /* the whole while(true) of solve() in one CTA.  Several ranks: all-gather the coarsest arrays once and replay all
          * rank-blocks on every rank (k_coarse_solve_blocks / _smem); one rank: the same kernel over the level's own arrays */
         int m[6];
@@ -1019,7 +1032,7 @@ static int op_solve_coarsest(S *s, int *iters, bool sync) {
         }
         return 0;
     }
-    if (d.n_proc == 1 || (!remote && !s->has_comm)) {
+    if ((d.n_proc == 1 || (!remote && !s->has_comm)) && one_cta) {
         BcPlan B;
         bc_plan(s, B);
         if ((B.bc_x_lo == FACE_WALL || B.bc_y_lo == FACE_WALL || B.bc_z_lo == FACE_WALL) && l != 0)
@@ -1035,7 +1048,11 @@ static int op_solve_coarsest(S *s, int *iters, bool sync) {
         }
         return 0;
     }
-    /* several ranks, legacy: host-driven loop, one halo exchange and one MAX all-reduce per iteration (d3:195,233) */
+    /* host-driven loop, one halo exchange and one MAX all-reduce per iteration (d3:195,233): the legacy multi-rank path and
+     * the path of coarsest levels too large for one CTA */
+    if (!one_cta && d.rank == 0 && getenv("SARASMG_VERBOSE"))
+        fprintf(stderr, "saras-mg: coarsest level has %d x %d x %d points per rank: host-driven solve loop (consider a deeper V-cycle)\n", L.v.nx, L.v.ny, L.v.nz);
+    if (s->capturing) return set_err("solve: the host-driven coarsest solve cannot be captured into a CUDA graph");
     int iterCount = 0;
     const long long cnt = (long long)L.v.nx * L.v.ny * L.v.nz;
     const unsigned nb = std::min(cdiv(cnt, 256), 1024u);
@@ -1109,14 +1126,15 @@ static int check_ipc_error(S *s) {
  * exchange numbers come from a device word, see IpcPlan), the NCCL all-gathers of the agglomerated coarsest solve and the
  * iteration-count read-back.  A graph is keyed by the level-buffer assignment (Jacobi ping-pong) and the profiling setup. */
 static unsigned graph_prof_key(const S *s) {
-    if (!(s->d.flags & (SARASMG_FLAG_PROFILE | SARASMG_FLAG_TIME_RUN))) return 0u;
-    return 1u + (unsigned)std::min(s->prof_max_level, 1000) + ((s->d.flags & SARASMG_FLAG_TIME_RUN) ? 100000u : 0u);
+    const unsigned sm = s->d.gs_smooth ? 0x40000000u : 0u;      /* sarasmg_set_smoother: one graph per smoother */
+    if (!(s->d.flags & (SARASMG_FLAG_PROFILE | SARASMG_FLAG_TIME_RUN))) return sm;
+    return sm + 1u + (unsigned)std::min(s->prof_max_level, 1000) + ((s->d.flags & SARASMG_FLAG_TIME_RUN) ? 100000u : 0u);
 }
 static int run_vcycle(S *s) {
     /* several ranks: the graph holds the NCCL all-gathers of the agglomerated coarsest solve and must be destroyed before
-     * the communicator (sarasmg_destroy).  Bit-exact on 2 GPUs; opt-in (SARASMG_GRAPH_MULTI=1) until run on 4 and 8 */
-    const bool capturable = s->use_graph && !s->gs_legacy &&
-                            (s->d.n_proc == 1 || (s->graph_multi && s->agg_ok && !s->coarse_legacy));
+     * the communicator (sarasmg_destroy) */
+    const bool capturable = s->use_graph && !s->gs_legacy && s->D > 0 &&    /* D == 0: the cycle is one smooth(); nothing to replay */
+                            coarse_in_one_cta(s) && (s->d.n_proc == 1 || (s->graph_multi && s->agg_ok && !s->coarse_legacy && s->ipc_ok));   /* the ncclSend/ncclRecv halo fallback stays eager */
     if (!capturable) return op_vcycle(s, nullptr);
     const double *key = s->lev[0].buf[SARASMG_PRESSURE];
     const unsigned pkey = graph_prof_key(s);
@@ -1182,32 +1200,34 @@ static int solve_core(S *s, const double *in_p, const double *in_rhs, int *cycle
         CU(cudaMemsetAsync(L.buf[SARASMG_RESIDUAL], 0, L.elems * sizeof(double), s->st));
     }
     const unsigned nbp = std::min(cdiv((long long)L0.v.Fx * L0.v.Fy, 2), 148u * 16u);
-    TRY(ensure_part(s, 2 * (size_t)nbp + 4096));
+    const long long shell = 2LL * L0.v.Fy * L0.v.Fz + 2LL * L0.v.nx * L0.v.Fz + 2LL * L0.v.nx * L0.v.ny;
+    const unsigned nbs = std::min(cdiv(shell, 256), 1024u);
+    TRY(ensure_part(s, 2 * (size_t)(nbp + nbs) + 4096));
     {
         ProfScope ps(s, SARASMG_K_MISC, 0);
+        /* compensated partial sums of the rhs core: part[2b], part[2b+1], b < nbp */
         k_load_inputs<<<nbp, 256, 0, s->st>>>(in_p, in_rhs, L0.buf[SARASMG_PRESSURE], L0.buf[SARASMG_RESIDUAL], L0.v, s->d_part);
         TRY(kcheck(s, "k_load_inputs"));
-        k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part, (int)nbp, 1, 0u, s->d_scal);      /* d_scal[0] = sum of the rhs core */
-        TRY(kcheck(s, "k_reduce_final"));
     }
     TRY(update_pads(s, 0, L0.buf[SARASMG_RESIDUAL]));       /* p:117 */
     TRY(update_pads(s, 0, L0.buf[SARASMG_PRESSURE]));       /* p:118 */
 
     if (!d.test_poisson) {                                  /* p:120-129 */
         ProfScope ps(s, SARASMG_K_MISC, 0);
-        const long long shell = 2LL * L0.v.Fy * L0.v.Fz + 2LL * L0.v.nx * L0.v.Fz + 2LL * L0.v.nx * L0.v.ny;
-        const unsigned nbs = std::min(cdiv(shell, 256), 1024u);
-        k_reduce_shell<<<nbs, 256, 0, s->st>>>(L0.buf[SARASMG_RESIDUAL], L0.v, s->d_part + nbp);
+        /* the pads' partial sums follow the core's, then ONE compensated reduction of all of them: d_scal[0] is the
+         * correctly rounded sum of the whole padded array (blitz::mean, p:122, is that sum / count) */
+        k_reduce_shell<<<nbs, 256, 0, s->st>>>(L0.buf[SARASMG_RESIDUAL], L0.v, s->d_part + 2 * (size_t)nbp);
         TRY(kcheck(s, "k_reduce_shell"));
-        k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part + nbp, (int)nbs, 1, 0u, s->d_scal + 1);   /* d_scal[1] = sum of the pads */
-        TRY(kcheck(s, "k_reduce_final"));
+        k_reduce_final_cs<<<1, 1024, 0, s->st>>>(s->d_part, (int)(nbp + nbs), s->d_scal);
+        TRY(kcheck(s, "k_reduce_final_cs"));
         std::vector<double> sums;
-        TRY(gather_scalars(s, 2, sums));
+        TRY(gather_scalars(s, 1, sums));
         const double cnt = (double)((long long)L0.v.Fx * L0.v.Fy * L0.v.Fz);
         double globalAvg = 0.0;
-        for (int r = 0; r < d.n_proc; r++) globalAvg += (sums[2 * r] + sums[2 * r + 1]) / cnt;      /* sum of local means, rank order */
+        for (int r = 0; r < d.n_proc; r++) globalAvg += sums[r] / cnt;      /* sum of local means, rank order (MPI_SUM, p:125) */
         globalAvg /= d.n_proc;
         if (s->mean_override) globalAvg = s->mean_value;
+        s->last_mean = globalAvg;
         k_sub_rows<<<nbp, 256, 0, s->st>>>(L0.buf[SARASMG_RESIDUAL], L0.v, globalAvg);
         TRY(kcheck(s, "k_sub_rows"));
     }
@@ -1223,7 +1243,7 @@ static int solve_core(S *s, const double *in_p, const double *in_rhs, int *cycle
         if (d.res_type == 0) CU(cudaStreamSynchronize(s->st));
         TRY(graph_prof_fold(s));                            /* the stream is idle here: computeError read its scalars back */
         s->last_coarse_iters = *s->h_iters;
-        if (s->last_coarse_iters > s->maxCount && (d.n_proc == 1 || (s->agg_ok && !s->coarse_legacy)) && d.print_residual && d.rank == 0)
+        if (s->last_coarse_iters > s->maxCount && coarse_in_one_cta(s) && (d.n_proc == 1 || (s->agg_ok && !s->coarse_legacy)) && d.print_residual && d.rank == 0)
             printf("WARNING: Iterations for solution at coarsest level not converging.\n");    /* d3:240-243 */
         if (hist) hist[i] = mgResidual;
         if (citers) citers[i] = s->last_coarse_iters;
@@ -1304,7 +1324,7 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     s->launches = 0;
     s->t_comp = s->t_tran = 0.0; s->bucket = 0;
     s->last_solve_ms = 0.0; s->last_coarse_iters = 0;
-    s->mean_override = 0; s->mean_value = 0.0;
+    s->mean_override = 0; s->mean_value = 0.0; s->last_mean = 0.0;
     s->prof_max_level = 1 << 20;
     s->gs_legacy = getenv("SARASMG_GS_LEGACY") != nullptr;
     s->no_pow2 = getenv("SARASMG_NO_POW2") != nullptr;
@@ -1317,7 +1337,7 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     for (int q = 0; q < 2; q++) s->xs[q] = s->xr[q] = s->ys[q] = s->yr[q] = nullptr;
     s->d_gather = nullptr;
     s->use_graph = getenv("SARASMG_NO_GRAPH") == nullptr;
-    s->graph_multi = getenv("SARASMG_GRAPH_MULTI") != nullptr;
+    s->graph_multi = !(getenv("SARASMG_GRAPH_MULTI") && atoi(getenv("SARASMG_GRAPH_MULTI")) == 0);   /* default on; SARASMG_GRAPH_MULTI=0: eager launches with several ranks */
     s->capturing = false; s->cap_sites = 0; s->cap_prof = nullptr; s->last_graph = nullptr;
     s->d_ipc_base = nullptr; s->ipc_base_h = 0;
     s->ipc_cta_max = getenv("SARASMG_IPC_CTA_MAX") ? atoll(getenv("SARASMG_IPC_CTA_MAX")) : 4096;
@@ -1546,31 +1566,39 @@ int sarasmg_download(sarasmg_handle s, double *p_out) {
     return 0;
 }
 
-/* page-lock a caller range once; failures (already pinned by the caller, unsupported memory) only cost speed */
-static void pin_range(S *s, const void *ptr, size_t bytes) {
-    for (auto &pr : s->pinned) if (pr.first == ptr && pr.second >= bytes) return;
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;
-    cudaGetLastError();
-    if (cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess) s->pinned.push_back({ptr, bytes});
-    else cudaGetLastError();
-}
-
+/* Page-locking of caller memory happens ONLY on request (sarasmg_host_register): the library cannot know how long a caller's
+ * buffer lives, and a registration that outlives its buffer is undefined behaviour.  The caller must unregister (or destroy
+ * the handle) before freeing the range. */
 int sarasmg_host_register(sarasmg_handle s, const void *ptr, unsigned long long bytes) {
     if (!s || !ptr) return set_err("sarasmg_host_register: null argument");
     CU(cudaSetDevice(s->d.device));
-    pin_range(s, ptr, (size_t)bytes);
+    for (auto &pr : s->pinned) if (pr.first == ptr && pr.second >= (size_t)bytes) return 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return 0;   /* already pinned by the caller */
+    cudaGetLastError();
+    cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), (size_t)bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err("sarasmg_host_register: %s", cudaGetErrorString(e)); }
+    s->pinned.push_back({ptr, (size_t)bytes});
     return 0;
+}
+
+int sarasmg_host_unregister(sarasmg_handle s, const void *ptr) {
+    if (!s || !ptr) return set_err("sarasmg_host_unregister: null argument");
+    CU(cudaSetDevice(s->d.device));
+    for (size_t q = 0; q < s->pinned.size(); q++)
+        if (s->pinned[q].first == ptr) {
+            CU(cudaStreamSynchronize(s->st));
+            cudaHostUnregister(const_cast<void *>(ptr));
+            cudaGetLastError();
+            s->pinned.erase(s->pinned.begin() + q);
+            return 0;
+        }
+    return 0;       /* not registered through this handle: nothing to do */
 }
 
 int sarasmg_solve(sarasmg_handle s, double *p_inout, const double *rhs, int *cycles_done, double *residual_history, int *coarse_iters) {
     if (!s || !p_inout || !rhs) return set_err("sarasmg_solve: null argument");
     CU(cudaSetDevice(s->d.device));
-    if (!getenv("SARASMG_NO_PIN")) {
-        const LevelView &v0 = s->lev[0].v;
-        const size_t bytes = (size_t)v0.Fx * v0.Fy * v0.Fz * sizeof(double);
-        if (bytes >= ((size_t)1 << 20)) { pin_range(s, p_inout, bytes); pin_range(s, rhs, bytes); }
-    }
     TRY(sarasmg_upload(s, p_inout, rhs));
     TRY(sarasmg_solve_resident(s, cycles_done, residual_history, coarse_iters));
     TRY(sarasmg_download(s, p_inout));
@@ -1834,9 +1862,19 @@ int sarasmg_debug_set_rhs_mean(sarasmg_handle s, int enable, double value) {
     s->mean_value = value;
     return 0;
 }
+int sarasmg_last_rhs_mean(sarasmg_handle s, double *value) {
+    if (!s || !value) return set_err("sarasmg_last_rhs_mean: null argument");
+    *value = s->last_mean;
+    return 0;
+}
 int sarasmg_set_vc_count(sarasmg_handle s, int count) {
     if (!s || count < 0) return set_err("sarasmg_set_vc_count: bad argument");
     s->d.vc_count = count;
+    return 0;
+}
+int sarasmg_set_smoother(sarasmg_handle s, int gs_smooth) {
+    if (!s) return set_err("sarasmg_set_smoother: null handle");
+    s->d.gs_smooth = gs_smooth ? 1 : 0;
     return 0;
 }
 int sarasmg_synchronize(sarasmg_handle s) { ENTER(s); CU(cudaStreamSynchronize(s->st)); return 0; }

@@ -219,6 +219,16 @@ void poisson::mgSolve(plainsf &inFn, const plainsf &rhs) {
     /* the device layer takes the compact padded layout; Blitz fields of SARAS are contiguous, views are staged */
     blitz::Array<real, 3> pHost = inFn.F.isStorageContiguous() ? inFn.F : inFn.F.copy();
     blitz::Array<real, 3> rHost = rhs.F.isStorageContiguous() ? rhs.F : rhs.F.copy();
+    /* page-lock the CALLER's field storage (SARAS allocates Pp / mgRHS once and hands the same objects in at every time
+     * step; they outlive this solver, hydro.h: base-class members vs the derived-class mgSolver) -- never the temporary
+     * staging copies above, whose storage dies at the end of this call.  Released in ~poisson. */
+    if (!getenv("SARASMG_NO_PIN")) {
+        const unsigned long long bytes = (unsigned long long)want(0) * want(1) * want(2) * sizeof(real);
+        if (bytes >= (1ull << 20)) {
+            if (inFn.F.isStorageContiguous()) pinField(inFn.F.dataFirst(), bytes);
+            if (rhs.F.isStorageContiguous()) pinField(rhs.F.dataFirst(), bytes);
+        }
+    }
 
     lastResiduals.assign(inputParams.vcCount > 0 ? inputParams.vcCount : 1, 0.0);
     lastCoarseIters.assign(lastResiduals.size(), 0);
@@ -238,6 +248,12 @@ void poisson::mgSolve(plainsf &inFn, const plainsf &rhs) {
         std::cout << std::endl;
     }
 #endif
+}
+
+void poisson::pinField(const void *ptr, unsigned long long bytes) {
+    for (const void *q : pinnedFields) if (q == ptr) return;
+    if (pinnedFields.size() >= 8) return;                   /* a solver sees two fields; never grow without bound */
+    if (sarasmg_host_register(device, ptr, bytes) == 0) pinnedFields.push_back(ptr);     /* failure only costs copy speed */
 }
 
 real poisson::testProlong() {
@@ -265,5 +281,8 @@ real poisson::testPeriodic() {
 
 poisson::~poisson() {
     /* under -DTIME_RUN the library prints the two "Time taken in ... within smooth" lines of poisson.cc:645-652 */
-    if (device) sarasmg_destroy(device);
+    if (device) {
+        for (const void *q : pinnedFields) sarasmg_host_unregister(device, q);
+        sarasmg_destroy(device);
+    }
 }

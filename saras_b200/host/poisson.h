@@ -44,6 +44,8 @@ class poisson {
     std::vector<double> xWall, yWall, zWall;
 
     sarasmg_solver_s *device;                       /* created at the first mgSolve */
+    std::vector<const void *> pinnedFields;         /* caller field storage page-locked by mgSolve, released in ~poisson */
+    void pinField(const void *ptr, unsigned long long bytes);
 
     void setLocalSizeIndex();
     void setStagBounds();

@@ -13,9 +13,13 @@ def pytest_configure(config):
 
 
 def _have_gpu():
+    """Device detection through the product library itself (ctypes -> sarasmg_device_count): the CUDA path has no torch
+    dependency, so a box with a CPU-only or missing torch must not turn the parity suite into silent skips."""
     try:
-        import torch
-        return torch.cuda.is_available()
+        import ctypes as C
+        from saras_b200 import capi
+        n = C.c_int(0)
+        return capi.load().sarasmg_device_count(C.byref(n)) == 0 and n.value > 0
     except Exception:
         return False
 
@@ -23,6 +27,8 @@ def _have_gpu():
 def pytest_collection_modifyitems(config, items):
     if _have_gpu():
         return
+    if os.environ.get("SARASMG_REQUIRE_GPU") and any("gpu" in item.keywords for item in items):
+        raise pytest.UsageError("SARASMG_REQUIRE_GPU is set but libsarasmg.so sees no CUDA device: refusing to skip the GPU parity tests")
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
         if "gpu" in item.keywords:

@@ -5,7 +5,7 @@ repository's (oracle/refbuild/Makefile, libsarasdropin_*.so, built only where /r
 GPU box with the snapshot).
 
 CPU: the libraries exist, load, report the right compile-time mode, and -- there being no GPU -- the call refuses loudly.
-GPU (opt-in until it has run once on a B200: SARASMG_TEST_DROPIN_REF=1): results against the oracle."""
+GPU: results against the oracle."""
 import os
 import subprocess
 import sys
@@ -54,8 +54,6 @@ def test_dropin_in_reference_refuses_without_gpu():
     dict(dim=2, test_poisson=1, xInd=6, zInd=6, vcDepth=4, vcCount=8, gsSmooth=1, resType=2),
 ], ids=["d3_testpoisson_gs", "d3_neumann_tanh_jacobi", "d2_testpoisson_gs"])
 def test_dropin_in_reference_matches_oracle(cfg):
-    if not os.environ.get("SARASMG_TEST_DROPIN_REF"):
-        pytest.skip("opt-in (SARASMG_TEST_DROPIN_REF=1) until this path has run once on a B200")
     if not sarasref.available(cfg["dim"], cfg.get("test_poisson", 0), dropin=True):
         pytest.skip("oracle/_ref/libsarasdropin_* not built")
     from oracle.mgoracle import Oracle
@@ -70,5 +68,6 @@ def test_dropin_in_reference_matches_oracle(cfg):
     np.testing.assert_allclose(rb["residuals"], ra["residuals"], rtol=1e-10, atol=0)
     if cfg.get("test_poisson"):
         assert np.array_equal(pa[0], pb[0])
-    else:       # the RHS mean is formed by a parallel sum on the device
-        assert np.max(np.abs(pa[0] - pb[0])) <= 1e-11 * np.max(np.abs(pa[0]))
+    else:       # the device forms the correctly rounded RHS mean (helpers.check_natural_mean_field)
+        from tests.helpers import check_natural_mean_field
+        check_natural_mean_field(o, p0, rhs, 0, pb[0], pa, "drop-in inside the reference's object model")

@@ -9,7 +9,7 @@ import pytest
 from oracle.mgoracle import Oracle
 from saras_b200 import host_api
 from tests.golden.cases import inputs
-from tests.helpers import max_abs, rel_linf
+from tests.helpers import max_abs, rel_linf, check_natural_mean_field
 
 pytestmark = pytest.mark.gpu
 
@@ -40,7 +40,7 @@ def test_dropin_mgsolve_vs_oracle(cfg):
         assert np.array_equal(got["coarse_iters"], ref["coarse_iters"])
         np.testing.assert_allclose(got["residuals"], ref["residuals"], rtol=1e-10, atol=0)
         if mode == "natural" and not cfg.get("test_poisson"):
-            assert rel_linf(p, p_ref) <= 1e-11
+            check_natural_mean_field(o, p0, rhs, 0, p, [p_ref], "drop-in")
         else:
             assert np.array_equal(p, p_ref), max_abs(p - p_ref)
     h.close()

@@ -2,7 +2,8 @@
 
 C1 (129^3 mgTest), C2 (257^2 LDC shape) and C3 (257^3 PPP, TGV shape) are small enough for the CPU oracle to finish in
 seconds, so they are compared with it directly: identical cycle and coarse-iteration counts, residual history, field.
-C4 (513^3, tanh-stretched) and C5 (1025^3) are checked through size-independent properties of the operator that hold
+C4 (513^3, tanh-stretched) is compared with the oracle directly too (2 cycles, about a minute of CPU per solve), and,
+like C5 (1025^3: a CPU run would need ~40 GB and hours), through size-independent properties of the operator that hold
 BIT FOR BIT in IEEE arithmetic:
   * scaling: every operation of the V-cycle commutes with multiplication by 2 (no rounding is involved), so with the
     data-dependent stopping tests disabled mgSolve(2 rhs) == 2 mgSolve(rhs) exactly;
@@ -80,6 +81,40 @@ def test_c3_tgv_257_ppp_against_oracle():
     ref = o.mg_solve([p_ref], [rhs.copy()])
     s.debug_set_rhs_mean(True, o.last_global_avg())
     got = s.mg_solve(p, rhs.copy())
+    assert got["cycles"] == ref["cycles"]
+    assert np.array_equal(got["coarse_iters"], ref["coarse_iters"])
+    np.testing.assert_allclose(got["residuals"], ref["residuals"], rtol=1e-10, atol=0)
+    assert np.array_equal(p, p_ref)
+    s.close()
+
+
+@pytest.mark.parametrize("gs,mean", [(1, "reference_mean_injected"), (0, "device_mean_vs_exact_mean_oracle")], ids=["gs", "jacobi"])
+def test_c4_rbc_513_tanh_against_oracle(gs, mean):
+    """BASELINE config 3 shape compared with the oracle DIRECTLY: 513^3, tanh-stretched in all three directions (closed
+    box, NNN), depth 6, V(2,2), production mode, 2 cycles (the -O3 IEEE-strict oracle needs under a minute per solve).
+    gs: the reference's sequential-sum mean is injected, everything bit-exact.  jacobi: the device forms the mean itself
+    (compensated sum over 1.4e8 values) and must match the oracle run with a correctly rounded mean bit for bit."""
+    if _host_mem_gb() < 24:
+        pytest.skip("needs ~14 GB of host memory")
+    cfg = dict(dim=3, xInd=9, yInd=9, zInd=9, vcDepth=6, vcCount=2, gsSmooth=gs, resType=2, mgTolerance=1e-6,
+               xGrid=2, yGrid=2, zGrid=2, betaX=1.2, betaY=1.2, betaZ=1.3)
+    o = Oracle(fast=True, **cfg)        # -O3, still -ffp-contract=off and no fast-math: same bits as the strict build
+    _, F = o.level_dims(0)
+    rhs = smooth_rhs(o, 0, F) + 0.1 + 0.01 * seeded_field(F, 11)
+    p0 = seeded_field(F, 12, 0.01)
+    if mean != "reference_mean_injected":
+        o.set_exact_mean(True)
+    p_ref = p0.copy()
+    ref = o.mg_solve([p_ref], [rhs.copy()])
+    avg = o.last_global_avg()
+    s = make_solver(o)                  # geometry (metrics, coefficients) is read from the oracle's setup
+    o.close()
+    if mean == "reference_mean_injected":
+        s.debug_set_rhs_mean(True, avg)
+    p = p0.copy()
+    got = s.mg_solve(p, rhs)
+    if mean != "reference_mean_injected":
+        assert s.last_rhs_mean() == avg
     assert got["cycles"] == ref["cycles"]
     assert np.array_equal(got["coarse_iters"], ref["coarse_iters"])
     np.testing.assert_allclose(got["residuals"], ref["residuals"], rtol=1e-10, atol=0)
