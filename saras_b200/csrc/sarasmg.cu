@@ -16,6 +16,7 @@
 #include "../../include/sarasmg.h"
 #include "mg_kernels.cuh"
 #include "gs_skew.cuh"
+#include "gs_strip.cuh"
 #include "mg_tma.cuh"
 
 #include <nccl.h>
@@ -61,10 +62,17 @@ struct Level {
     LevelView v;
     bool x_uniform;         /* xix2 has one value over the core: the smoother's diagonal does not change along an x-march */
     bool z_uniform;         /* ztz2 has one value over the core: the diagonal does not change along a z column */
+    bool zz_uniform;        /* ztz2 and ztzz each have one value over the core */
     GsPlan gs;              /* skewed Gauss-Seidel sweep: task table + progress counters (device) */
     int4 *gs_tasks;
     int *gs_sync;
     size_t gs_smem;
+    GsStripPlan gss;        /* warp-strip Gauss-Seidel sweep of the large 3-D levels (gs_strip.cuh) */
+    int2 *gss_tasks;
+    int *gss_sync;
+    double *gss_rden, *gss_xpair;
+    size_t gss_smem;
+    bool gss_ok;
     double *buf[3];         /* SARASMG_PRESSURE, SARASMG_RESIDUAL, SARASMG_TMP */
     CUtensorMap tmapP[3];   /* TMA descriptors of the three arrays for the pressure box (with halo ring) ... */
     CUtensorMap tmapR[3];   /* ... and for the right-hand-side box; swapped together with buf[] */
@@ -593,11 +601,107 @@ static int build_gs_plan(S *s, Level &L) {
     return 0;
 }
 
+/* geometry of the warp-strip Gauss-Seidel kernel for one level (gs_strip.cuh): quads per slab, prefetch distance and warps
+ * per CTA are chosen so that every tile is resident at once (one CTA per SM: a tile holds its SM for the whole sweep, a
+ * second wave would double the sweep time) with as many compute warps as possible */
+static int build_gs_strip_plan(S *s, Level &L) {
+    L.gss_ok = false; L.gss_tasks = nullptr; L.gss_sync = nullptr; L.gss_rden = nullptr; L.gss_xpair = nullptr; L.gss_smem = 0;
+    const LevelView &v = L.v;
+    if (s->planar) return 0;
+    /* OPT-IN (SARASMG_GS_STRIP=1).  Bit-exact, but measured slower than k_gs_skew on B200 (1025^3 sweep: 15-21 ms against
+     * 11 ms, profiles/r02_gs_strip_*.txt): both kernels are bound by warps-per-SM / instruction latency, not by HBM, and the
+     * window rings of this one leave room for only 11-13 warps per SM.  Kept for the analysis in DESIGN.md and as the
+     * starting point of the next attempt. */
+    {
+        const char *e = getenv("SARASMG_GS_STRIP");
+        if (!e || atoi(e) == 0) return 0;
+    }
+    int min_n = 200;                                    /* below this the start-up skew of the strip pipeline outweighs its gain */
+    if (const char *e = getenv("SARASMG_GS_STRIP_MIN")) min_n = atoi(e);
+    if (v.nx < min_n || v.ny < 32 || v.nz < 16) return 0;
+    int dev = 0, nsm = 148, smem_max = 227 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int budget = smem_max - 1024;                 /* static control block + alignment */
+    const int NQ = (v.nz + 3) / 4, NJ = (v.ny + 31) / 32;
+    const int f_nq = getenv("SARASMG_GSS_NQ") ? atoi(getenv("SARASMG_GSS_NQ")) : 0;
+    const int f_dp = getenv("SARASMG_GSS_DP") ? atoi(getenv("SARASMG_GSS_DP")) : 0;
+    const int f_wc = getenv("SARASMG_GSS_WC") ? atoi(getenv("SARASMG_GSS_WC")) : 0;
+    long long best = -1;
+    GsStripPlan B;
+    memset(&B, 0, sizeof(B));
+    for (int DP = 3; DP >= 2; DP--) {
+        if (f_dp && DP != f_dp) continue;
+        for (int nq = 1; nq <= 16; nq++) {
+            if (f_nq && nq != f_nq) continue;
+            const int bytes = gss_warp_bytes(nq, DP);
+            int wcmax = std::min(GSS_MAXW, budget / bytes);
+            if (f_wc) wcmax = std::min(wcmax, f_wc);
+            if (wcmax < 1) continue;
+            const int NZW = (NQ + nq - 1) / nq;
+            const int NG = (NZW + wcmax - 1) / wcmax;
+            const int WC = (NZW + NG - 1) / NG;
+            if ((long long)NJ * NG > nsm && !f_nq) continue;
+            /* more warps hide more latency; among equal counts prefer the deeper prefetch, then the taller slab */
+            const long long score = (long long)NJ * NZW * 1000 + DP * 20 + nq;
+            if (score > best) {
+                best = score;
+                B.NJ = NJ; B.NZW = NZW; B.NG = NG; B.nq = nq; B.NQ = NQ; B.WC = WC; B.DP = DP;
+                B.RW = 2 * nq + DP + 1; B.RRn = DP + 1; B.ntasks = NJ * NG;
+                B.warp_bytes = gss_warp_bytes(nq, DP);
+            }
+        }
+    }
+    if (best < 0) return 0;
+    B.z_uniform = L.zz_uniform ? 1 : 0;
+    B.two_h = 2.0 * v.hxhyhz;
+    CU(cudaMalloc(&L.gss_xpair, sizeof(double) * 2 * (size_t)v.nx));
+    k_gss_xpair<<<cdiv(v.nx, 256), 256, 0, s->st>>>(v, L.gss_xpair);
+    TRY(kcheck(s, "k_gss_xpair"));
+    B.xpair = L.gss_xpair;
+    B.rden = nullptr;
+    if (B.z_uniform) {
+        CU(cudaMalloc(&L.gss_rden, sizeof(double) * (size_t)v.nx * v.ny));
+        k_gss_rden<<<std::min(cdiv((long long)v.nx * v.ny, 256), 2048u), 256, 0, s->st>>>(v, L.gss_rden);
+        TRY(kcheck(s, "k_gss_rden"));
+        B.rden = L.gss_rden;
+    }
+    /* ticket order: ideal start step of a tile (strip J starts 32 steps after J-1, a slab nq steps after the one below) */
+    struct T { long long key; int J, G; };
+    std::vector<T> ts;
+    for (int g = 0; g < B.NG; g++)
+        for (int J = 0; J < B.NJ; J++) ts.push_back({32LL * J + (long long)B.nq * B.WC * g, J, g});
+    std::stable_sort(ts.begin(), ts.end(), [](const T &a, const T &b) { return a.key < b.key; });
+    std::vector<int2> ht(B.ntasks);
+    for (int q = 0; q < B.ntasks; q++) ht[q] = make_int2(ts[q].J, ts[q].G);
+    CU(cudaMalloc(&L.gss_tasks, sizeof(int2) * B.ntasks));
+    CU(cudaMemcpyAsync(L.gss_tasks, ht.data(), sizeof(int2) * B.ntasks, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMalloc(&L.gss_sync, sizeof(int) * ((size_t)B.NJ * B.NZW + 1)));
+    CU(cudaStreamSynchronize(s->st));
+    B.tasks = L.gss_tasks; B.sync = L.gss_sync;
+    L.gss = B;
+    L.gss_smem = (size_t)B.WC * B.warp_bytes;
+    L.gss_ok = true;
+    if (getenv("SARASMG_VERBOSE") && s->d.rank == 0)
+        fprintf(stderr, "saras-mg: strip GS on %dx%dx%d: %d strips x %d slabs of %d quads, %d CTAs x %d warps, DP %d, %zu B smem\n",
+                v.nx, v.ny, v.nz, B.NJ, B.NZW, B.nq, B.ntasks, B.WC, B.DP, L.gss_smem);
+    return 0;
+}
+
 static int gs_sweep(S *s, int level) {
     Level &L = s->lev[level];
     const LevelView &v = L.v;
     double *P = L.buf[SARASMG_PRESSURE];
     const double *R = L.buf[SARASMG_RESIDUAL];
+    if (!s->gs_legacy && L.gss_ok) {
+        /* large 3-D level: warp-strip pipeline (gs_strip.cuh) */
+        const GsStripPlan &G = L.gss;
+        CU(cudaMemsetAsync(L.gss_sync, 0, sizeof(int) * ((size_t)G.NJ * G.NZW + 1), s->st));
+        if (G.z_uniform) k_gs_strip<true><<<G.ntasks, dim3(32, G.WC + 1, 1), L.gss_smem, s->st>>>(P, R, v, G);
+        else k_gs_strip<false><<<G.ntasks, dim3(32, G.WC + 1, 1), L.gss_smem, s->st>>>(P, R, v, G);
+        return kcheck(s, "k_gs_strip");
+    }
     if (!s->gs_legacy) {
         /* one launch per sweep: skewed pipeline with ticketed tile tasks (gs_skew.cuh) */
         const GsPlan &G = L.gs;
@@ -1397,11 +1501,18 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
             L.z_uniform = true;
             for (int k = 1; k < v.nz; k++) if (a[k] != a[0]) { L.z_uniform = false; break; }
         }
+        L.zz_uniform = L.z_uniform && desc->ztzz;           /* ... and so has ztzz: the strip Gauss-Seidel kernel then needs no z tables */
+        if (L.zz_uniform) {
+            const double *a = desc->ztzz + moff[2] + 1;
+            for (int k = 1; k < v.nz; k++) if (a[k] != a[0]) { L.zz_uniform = false; break; }
+        }
         L.gs_tasks = nullptr; L.gs_sync = nullptr; L.gs_smem = 0;
+        L.gss_tasks = nullptr; L.gss_sync = nullptr; L.gss_rden = nullptr; L.gss_xpair = nullptr; L.gss_smem = 0; L.gss_ok = false;
         for (int dd = 0; dd < 3; dd++) moff[dd] += (size_t)Fd[dd];
         v.xixx = L.met[0] + 1; v.xix2 = L.met[1] + 1; v.etyy = L.met[2] + 1; v.ety2 = L.met[3] + 1; v.ztzz = L.met[4] + 1; v.ztz2 = L.met[5] + 1;
     }
     for (int l = 0; l <= D; l++) TRY(build_gs_plan(s, s->lev[l]));
+    for (int l = 0; l <= D; l++) TRY(build_gs_strip_plan(s, s->lev[l]));
     for (int l = 0; l <= D; l++) TRY(make_level_tmaps(s, s->lev[l]));
     CU(cudaFuncSetAttribute(k_coarse_solve_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_coarse_solve_smem<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1413,6 +1524,13 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     CU(cudaFuncSetAttribute(k_stencil_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
     CU(cudaFuncSetAttribute(k_gs_skew<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_gs_skew<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    {
+        int dev = 0, smem_max = 227 * 1024;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        CU(cudaFuncSetAttribute(k_gs_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024));
+        CU(cudaFuncSetAttribute(k_gs_strip<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024));
+    }
     {   /* p:360-361 maxCount */
         const LevelView &v = s->lev[D].v;
         s->maxCount = (v.Fx - 1) * (v.Fy - 1) * (v.Fz - 1);
@@ -1505,6 +1623,7 @@ int sarasmg_destroy(sarasmg_handle s) {
         for (int a = 0; a < 3; a++) cudaFree(L.buf[a]);
         for (int m = 0; m < 6; m++) cudaFree(L.met[m]);
         cudaFree(L.gs_tasks); cudaFree(L.gs_sync);
+        cudaFree(L.gss_tasks); cudaFree(L.gss_sync); cudaFree(L.gss_rden); cudaFree(L.gss_xpair);
     }
     for (int q = 0; q < 3; q++) if (s->d_wall[q]) cudaFree(s->d_wall[q]);
     for (int q = 0; q < 2; q++) { cudaFree(s->xs[q]); cudaFree(s->xr[q]); cudaFree(s->ys[q]); cudaFree(s->yr[q]); }

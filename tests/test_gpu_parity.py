@@ -326,3 +326,59 @@ def test_graph_replay_equals_eager_launches(monkeypatch):
     assert np.array_equal(outs[0][1]["residuals"], outs[1][1]["residuals"])
     assert np.array_equal(outs[0][1]["coarse_iters"], outs[1][1]["coarse_iters"])
     assert outs[0][1]["cycles"] == outs[1][1]["cycles"] and outs[0][2]["cycles"] == outs[1][2]["cycles"]
+
+
+# ---- warp-strip Gauss-Seidel kernel (gs_strip.cuh): production path of the large 3-D levels, forced onto small grids ----
+STRIP_GRIDS = [
+    # 33 x 65 x 33: three strips (32 + 32 + 1 columns), 9 quads with ONE live point in the last one
+    dict(name="uni_nnn", dim=3, xInd=5, yInd=6, zInd=5, vcDepth=1),
+    dict(name="tanh_all", dim=3, xInd=5, yInd=6, zInd=5, vcDepth=1, xGrid=2, yGrid=2, zGrid=2, betaX=1.2, betaY=0.9, betaZ=1.4),
+    dict(name="ppp", dim=3, xInd=4, yInd=6, zInd=6, vcDepth=1, xPer=1, yPer=1, zPer=1),
+    dict(name="testpoisson", dim=3, xInd=4, yInd=5, zInd=5, vcDepth=1, test_poisson=1),
+]
+STRIP_GEOMS = [       # quads per slab, prefetch distance, compute warps per CTA
+    dict(nq=1, dp=2, wc=13), dict(nq=2, dp=2, wc=2), dict(nq=2, dp=3, wc=3), dict(nq=3, dp=2, wc=1),
+    dict(nq=4, dp=3, wc=13), dict(nq=5, dp=2, wc=2), dict(nq=16, dp=2, wc=4),
+]
+
+
+@pytest.mark.parametrize("grid", STRIP_GRIDS, ids=lambda c: c["name"])
+@pytest.mark.parametrize("geom", STRIP_GEOMS, ids=lambda g: "nq%d_dp%d_wc%d" % (g["nq"], g["dp"], g["wc"]))
+def test_gs_strip_smooth_bitexact(grid, geom, monkeypatch):
+    """lexicographic Gauss-Seidel sweeps of k_gs_strip against the oracle, for slab heights that divide the column, leave a
+    remainder, exceed it; one CTA per strip and several (the -z hand-off through shared memory and through global memory)"""
+    monkeypatch.setenv("SARASMG_GS_STRIP", "1")
+    monkeypatch.setenv("SARASMG_GS_STRIP_MIN", "8")
+    monkeypatch.setenv("SARASMG_GSS_NQ", str(geom["nq"]))
+    monkeypatch.setenv("SARASMG_GSS_DP", str(geom["dp"]))
+    monkeypatch.setenv("SARASMG_GSS_WC", str(geom["wc"]))
+    o, s = _mk(grid, gsSmooth=1)
+    _, F = o.level_dims(0)
+    _load_both(o, s, 0, mo.PRESSURE, seeded_field(F, 310))
+    _load_both(o, s, 0, mo.RESIDUAL, seeded_field(F, 311, 5.0))
+    for count in (1, 3):
+        o.set_level(0); o.set_zero_bc(0); o.smooth(count)
+        s.set_level(0); s.set_zero_bc(0); s.smooth(count)
+        ref = o.array(0, 0, mo.PRESSURE)
+        got = s.level_get(0, capi.PRESSURE)
+        assert np.array_equal(got, ref), "count %d: %d points differ, max %g" % (count, int(np.sum(got != ref)), max_abs(got - ref))
+    s.close()
+
+
+def test_gs_strip_default_geometry_257_against_oracle(monkeypatch):
+    """the geometry the library picks by itself on a level that qualifies (257 x 65 x 257: default threshold), whole mgSolve"""
+    monkeypatch.setenv("SARASMG_GS_STRIP", "1")
+    cfg = dict(name="strip257", dim=3, xInd=8, yInd=6, zInd=8, vcDepth=4, vcCount=3, gsSmooth=1, resType=2, zGrid=2, betaZ=1.2)
+    o, s = _mk(cfg)
+    _, F = o.level_dims(0)
+    rhs = smooth_rhs(o, 0, F) + 0.2
+    p0 = seeded_field(F, 9, 0.01)
+    p_ref = p0.copy()
+    ref = o.mg_solve([p_ref], [rhs.copy()])
+    s.debug_set_rhs_mean(True, o.last_global_avg())
+    p = p0.copy()
+    got = s.mg_solve(p, rhs.copy())
+    assert got["cycles"] == ref["cycles"] and np.array_equal(got["coarse_iters"], ref["coarse_iters"])
+    np.testing.assert_allclose(got["residuals"], ref["residuals"], rtol=1e-10, atol=0)
+    assert np.array_equal(p, p_ref), max_abs(p - p_ref)
+    s.close()
