@@ -104,6 +104,32 @@ int sarasmg_solve(sarasmg_handle h, double *p_inout, const double *rhs,
 int sarasmg_upload(sarasmg_handle h, const double *p_in, const double *rhs);
 int sarasmg_solve_resident(sarasmg_handle h, int *cycles_done, double *residual_history, int *coarse_iters);
 int sarasmg_download(sarasmg_handle h, double *p_out);
+/* ---- the projection step around mgSolve, device-resident ------------------------------------------------
+ * hydro_d3::timeAdvance brackets the solve with two bandwidth-bound field operations (hydro_d3.cc:326-327, 347-362):
+ *     V.divergence(mgRHS, P);  mgRHS *= 1.0/dt;                      lib/field/vfield.cc:299-320
+ *     mgSolver.mgSolve(Pp, mgRHS);
+ *     Pp.syncData();  P += Pp;                                       lib/parallel/mpidata.cc:278-306, lib/field/sfield.cc:197-201
+ *     Pp.gradient(pressureGradient, V);  pressureGradient *= dt;  V -= pressureGradient;      lib/field/plainsf.h:92-98
+ * With host fields every solve pays two PCIe crossings of Pp / mgRHS.  These entries keep V, P, Pp and mgRHS on the
+ * device: the caller uploads the velocity once (or after its own host-side stages), then each sarasmg_proj_step runs
+ * divergence -> mgSolve -> correction without touching the host; Pp stays resident as the next step's initial guess.
+ * Field layouts are the reference's Blitz arrays (base -1, z fastest; lib/field/field.cc:66-105): Vx (nx+1, ny+2, nz+2),
+ * Vy (nx+2, ny+1, nz+2), Vz (nx+2, ny+2, nz+1), P / Pp / mgRHS (nx+2, ny+2, nz+2), nx.. = n0[] of the descriptor.
+ * One rank only for now (Pp.syncData between ranks is row 8f-2), multigrid_d3 only. */
+typedef struct {
+    const double *xi_x_staggr, *et_y_staggr, *zt_z_staggr;   /* grid::xi_xStaggr ..: n_d + 2 doubles, first entry is index -1 */
+    const double *xi_x_colloc, *et_y_colloc, *zt_z_colloc;   /* grid::xi_xColloc ..: n_d + 1 doubles, first entry is index -1 */
+    double d_xi, d_et, d_zt;                                 /* grid::dXi, dEt, dZt */
+} sarasmg_proj_desc;
+enum { SARASMG_PROJ_VX = 0, SARASMG_PROJ_VY = 1, SARASMG_PROJ_VZ = 2, SARASMG_PROJ_P = 3, SARASMG_PROJ_PP = 4, SARASMG_PROJ_RHS = 5 };
+int sarasmg_proj_setup(sarasmg_handle h, const sarasmg_proj_desc *desc);
+int sarasmg_proj_upload(sarasmg_handle h, int which, const double *host);      /* VX, VY, VZ, P, PP */
+int sarasmg_proj_download(sarasmg_handle h, int which, double *host);          /* ... and RHS */
+int sarasmg_proj_divergence(sarasmg_handle h, double inv_dt);                  /* mgRHS = div(V) * inv_dt       vfield.cc:299-320, hydro_d3.cc:327 */
+int sarasmg_proj_correct(sarasmg_handle h, double dt);                         /* Pp = solution; syncData; P += Pp; V -= dt grad(Pp)   hydro_d3.cc:347-362 */
+/* divergence -> mgSolve -> correction in one call; history arguments as in sarasmg_solve */
+int sarasmg_proj_step(sarasmg_handle h, double dt, int *cycles_done, double *residual_history, int *coarse_iters);
+
 /* TEST_POISSON epilogue (poisson.cc:153-204): max |analytic - pressureData(0)| over the core, all ranks */
 int sarasmg_analytic_deviation(sarasmg_handle h, double *max_dev);
 

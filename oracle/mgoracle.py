@@ -48,8 +48,8 @@ def _load(fast=False):
         return _LIBS[key]
     name = "libmgoracle_fast.so" if fast else "libmgoracle.so"
     path = os.path.join(_HERE, "_build", name)
-    src = os.path.join(_HERE, "mg_oracle.c")
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("mg_oracle.c", "proj_oracle.c")]
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(f) for f in srcs):
         build(fast)
     lib = C.CDLL(path)
     vp, ip, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -85,6 +85,11 @@ def _load(fast=False):
     lib.mgo_last_global_avg.restype = C.c_double
     lib.mgo_last_global_avg.argtypes = [vp]
     lib.mgo_set_exact_mean.argtypes = [vp, C.c_int]
+    lib.projo_colloc_metric.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp]
+    lib.projo_staggr_metric.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp]
+    lib.projo_divergence.argtypes = [C.c_int] * 3 + [dp] * 6 + [C.c_double] * 4 + [dp]
+    lib.projo_sync_one_rank.argtypes = [C.c_int] * 5 + [dp]
+    lib.projo_correct.argtypes = [C.c_int] * 5 + [dp] * 8 + [C.c_double] * 4
     lib.mgo_lup_count.argtypes = [vp]
     _LIBS[key] = lib
     return lib
@@ -246,3 +251,49 @@ class Oracle:
                                        iters.ctypes.data_as(C.POINTER(C.c_int)), C.byref(dev))
         return dict(cycles=cycles, residuals=hist[:cycles].copy(), coarse_iters=iters[:cycles].copy(),
                     max_dev=dev.value)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# projection-step oracle (oracle/proj_oracle.c): vfield::divergence, Pp.syncData / P += Pp / V -= dt grad(Pp)
+# ---------------------------------------------------------------------------------------------------------------------
+def _dpp(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def proj_shapes(n):
+    nx, ny, nz = n
+    return dict(vx=(nx + 1, ny + 2, nz + 2), vy=(nx + 2, ny + 1, nz + 2), vz=(nx + 2, ny + 2, nz + 1), sc=(nx + 2, ny + 2, nz + 2))
+
+
+def proj_metrics(o, rank=0):
+    """first-derivative metrics of rank `rank` of Oracle `o`: (staggered xi_x, et_y, zt_z), (collocated ...), (dXi, dEt, dZt).
+    grid.cc:404-421 (uniform) and 442-519 (tanh), restated in oracle/proj_oracle.c."""
+    lib = _load()
+    c = o.cfg
+    n0, _ = o.level_dims(0)
+    info = o.rank_info(rank)
+    spacing = o.spacing()
+    stag, coll = [], []
+    starts = [info["xRank"] * (n0[0] - 1), info["yRank"] * (n0[1] - 1), 0]
+    for d, (gt, beta, ln) in enumerate(((c["xGrid"], c["betaX"], c["Lx"]), (c["yGrid"], c["betaY"], c["Ly"]), (c["zGrid"], c["betaZ"], c["Lz"]))):
+        out = np.zeros(n0[d] + 1)
+        lib.projo_colloc_metric(n0[d], starts[d], gt, beta, ln, spacing[d], _dpp(out))
+        coll.append(out)
+        s = np.zeros(n0[d] + 2)
+        lib.projo_staggr_metric(n0[d], starts[d], gt, beta, ln, spacing[d], _dpp(s))
+        stag.append(s)
+    return stag, coll, spacing
+
+
+def proj_divergence(n, vx, vy, vz, stag, spacing, inv_dt):
+    rhs = np.zeros(proj_shapes(n)["sc"])
+    _load().projo_divergence(n[0], n[1], n[2], _dpp(vx), _dpp(vy), _dpp(vz), _dpp(stag[0]), _dpp(stag[1]), _dpp(stag[2]),
+                             spacing[0], spacing[1], spacing[2], inv_dt, _dpp(rhs))
+    return rhs
+
+
+def proj_correct(n, xper, yper, pp, P, vx, vy, vz, coll, spacing, dt):
+    """in place on pp (syncData), P, vx, vy, vz"""
+    _load().projo_correct(n[0], n[1], n[2], int(xper), int(yper), _dpp(pp), _dpp(P), _dpp(vx), _dpp(vy), _dpp(vz),
+                          _dpp(coll[0]), _dpp(coll[1]), _dpp(coll[2]), spacing[0], spacing[1], spacing[2], dt)

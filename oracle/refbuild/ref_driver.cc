@@ -68,6 +68,8 @@ struct Job {
     int mode;                 /* 0 mgSolve, 1 setup only */
     double *res_hist;         /* SARAS_DROPIN: residual history and cycle count taken from the drop-in object (rank 0) */
     int *cycles;
+    double *proj_out;         /* mode 2: per rank xi_xStaggr, et_yStaggr, zt_zStaggr (F_d each), xi_xColloc, et_yColloc, zt_zColloc
+                                 (F_d - 1 each), then dXi, dEt, dZt -- the first-derivative metrics of the projection step */
 };
 
 #ifdef PLANAR
@@ -156,7 +158,16 @@ void rank_main(void *arg) {
 #endif
         }
     }
-    if (job->mode == 1) return;
+    if (job->mode == 2 && job->proj_out) {
+        const blitz::Array<real, 1> *m[6] = {&gridData.xi_xStaggr, &gridData.et_yStaggr, &gridData.zt_zStaggr,
+                                              &gridData.xi_xColloc, &gridData.et_yColloc, &gridData.zt_zColloc};
+        size_t per_rank = 3;
+        for (int q = 0; q < 6; q++) per_rank += m[q]->size();
+        double *o = job->proj_out + (size_t)r * per_rank;
+        for (int q = 0; q < 6; q++) for (int i = m[q]->lbound(0); i <= m[q]->ubound(0); i++) *o++ = (*m[q])(i);
+        *o++ = gridData.dXi; *o++ = gridData.dEt; *o++ = gridData.dZt;
+    }
+    if (job->mode >= 1) return;
 
     plainsf Pp(gridData), mgRHS(gridData);
     const size_t n = Pp.F.size();
@@ -194,7 +205,8 @@ int sarasref_mode(void) {
 /* Runs the reference mgSolve on npX*npY thread-ranks.  p_inout[r] / rhs[r]: padded level-0 arrays of rank r.
  * res_hist[>= vcCount] receives the values printed as "Residual after V Cycle i is X" (17 significant digits),
  * max_dev the TEST_POISSON "Maximum absolute deviation" line (6 digits, as printed).  Returns the number of V-cycles
- * the reference ran, or -1 on error. */
+ * the reference ran, or -1 on error.  mode 1: setup only (metrics_out / coef_out); mode 2: setup only, metrics_out receives the
+ * first-derivative metrics of grid.cc (layout at Job::proj_out). */
 int sarasref_mg_solve(const char *workdir, const ref_params *prm, double *const *p_inout, const double *const *rhs,
                       double *res_hist, double *max_dev, double *metrics_out, double *coef_out, int mode) {
     write_yaml(*prm, workdir);
@@ -207,7 +219,7 @@ int sarasref_mg_solve(const char *workdir, const ref_params *prm, double *const 
     const std::streamsize oldprec = std::cout.precision(17);
 
     int dropin_cycles = -1;
-    Job job = {prm, p_inout, rhs, metrics_out, coef_out, mode, res_hist, &dropin_cycles};
+    Job job = {prm, p_inout, rhs, mode == 2 ? nullptr : metrics_out, coef_out, mode, res_hist, &dropin_cycles, mode == 2 ? metrics_out : nullptr};
     saras_mpi_run(prm->npX * prm->npY, rank_main, &job);
 
     std::cout.rdbuf(old);

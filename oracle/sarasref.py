@@ -116,3 +116,32 @@ def setup_data(**kw):
             pos += n
         out.append(d)
     return out, coef.reshape(cfg["vcDepth"] + 1, 9)
+
+
+def proj_metrics(**kw):
+    """First-derivative metrics of every rank as the reference's grid object holds them (grid.cc:370-519): per rank a dict with
+    xi_xStaggr, et_yStaggr, zt_zStaggr (index -1 .. n), xi_xColloc, et_yColloc, zt_zColloc (index -1 .. n-1) and (dXi, dEt, dZt)."""
+    cfg = _cfg(kw)
+    lib = _load(cfg["dim"], cfg["test_poisson"], False)
+    nr = cfg["npX"] * cfg["npY"]
+    F = level0_extents(cfg)
+    per_rank = sum(F) + sum(f - 1 for f in F) + 3
+    buf = np.zeros(nr * per_rank, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    prm = MgoParams(**cfg)
+    with tempfile.TemporaryDirectory() as wd:
+        rc = lib.sarasref_mg_solve(wd.encode(), C.byref(prm), None, None, None, None, buf.ctypes.data_as(dp), None, 2)
+    if rc < 0:
+        raise RuntimeError("sarasref setup failed")
+    out = []
+    for r in range(nr):
+        o = buf[r * per_rank:(r + 1) * per_rank]
+        pos = 0
+        d = {}
+        for q, name in enumerate(["xi_xStaggr", "et_yStaggr", "zt_zStaggr", "xi_xColloc", "et_yColloc", "zt_zColloc"]):
+            n = F[q % 3] - (1 if q >= 3 else 0)
+            d[name] = o[pos:pos + n].copy()
+            pos += n
+        d["spacing"] = tuple(o[pos:pos + 3])
+        out.append(d)
+    return out

@@ -39,6 +39,14 @@ class Desc(C.Structure):
     ]
 
 
+class ProjDesc(C.Structure):
+    _fields_ = [("xi_x_staggr", _dp), ("et_y_staggr", _dp), ("zt_z_staggr", _dp),
+                ("xi_x_colloc", _dp), ("et_y_colloc", _dp), ("zt_z_colloc", _dp),
+                ("d_xi", C.c_double), ("d_et", C.c_double), ("d_zt", C.c_double)]
+
+
+PROJ_VX, PROJ_VY, PROJ_VZ, PROJ_P, PROJ_PP, PROJ_RHS = range(6)
+
 _lib = None
 
 SYMBOLS = [
@@ -52,6 +60,7 @@ SYMBOLS = [
     "sarasmg_last_solve_ms", "sarasmg_synchronize", "sarasmg_debug_set_rhs_mean",
     "sarasmg_set_profile_max_level", "sarasmg_event_record", "sarasmg_event_elapsed_ms", "sarasmg_host_register",
     "sarasmg_set_vc_count", "sarasmg_host_unregister", "sarasmg_set_smoother", "sarasmg_last_rhs_mean",
+    "sarasmg_proj_setup", "sarasmg_proj_upload", "sarasmg_proj_download", "sarasmg_proj_divergence", "sarasmg_proj_correct", "sarasmg_proj_step",
 ]
 
 
@@ -105,6 +114,12 @@ def load():
     lib.sarasmg_host_unregister.argtypes = [vp, C.c_void_p]
     lib.sarasmg_set_smoother.argtypes = [vp, C.c_int]
     lib.sarasmg_last_rhs_mean.argtypes = [vp, _dp]
+    lib.sarasmg_proj_setup.argtypes = [vp, C.POINTER(ProjDesc)]
+    lib.sarasmg_proj_upload.argtypes = [vp, C.c_int, _dp]
+    lib.sarasmg_proj_download.argtypes = [vp, C.c_int, _dp]
+    lib.sarasmg_proj_divergence.argtypes = [vp, C.c_double]
+    lib.sarasmg_proj_correct.argtypes = [vp, C.c_double]
+    lib.sarasmg_proj_step.argtypes = [vp, C.c_double, ip, _dp, ip]
     _lib = lib
     return lib
 
@@ -336,6 +351,43 @@ class Solver:
 
     def debug_set_rhs_mean(self, enable, value=0.0):
         self._check(self.lib.sarasmg_debug_set_rhs_mean(self.h, int(enable), float(value)))
+
+    # -- device-resident projection step ---------------------------------------------
+    def proj_shapes(self):
+        n, _ = self.level_dims(0)
+        nx, ny, nz = n
+        return [(nx + 1, ny + 2, nz + 2), (nx + 2, ny + 1, nz + 2), (nx + 2, ny + 2, nz + 1), (nx + 2, ny + 2, nz + 2),
+                (nx + 2, ny + 2, nz + 2), (nx + 2, ny + 2, nz + 2)]
+
+    def proj_setup(self, staggr, colloc, spacing):
+        """staggr / colloc: three 1-D arrays each (xi_x, et_y, zt_z at staggered / collocated points, first entry = index -1)"""
+        d = ProjDesc()
+        self._proj_keep = [_f64(a) for a in list(staggr) + list(colloc)]
+        for name, a in zip(("xi_x_staggr", "et_y_staggr", "zt_z_staggr", "xi_x_colloc", "et_y_colloc", "zt_z_colloc"), self._proj_keep):
+            setattr(d, name, _ptr(a))
+        d.d_xi, d.d_et, d.d_zt = [float(v) for v in spacing]
+        self._check(self.lib.sarasmg_proj_setup(self.h, C.byref(d)))
+
+    def proj_upload(self, which, a):
+        a = _f64(a)
+        assert a.shape == self.proj_shapes()[which], (a.shape, self.proj_shapes()[which])
+        self._check(self.lib.sarasmg_proj_upload(self.h, which, _ptr(a)))
+
+    def proj_download(self, which):
+        a = np.zeros(self.proj_shapes()[which], dtype=np.float64)
+        self._check(self.lib.sarasmg_proj_download(self.h, which, _ptr(a)))
+        return a
+
+    def proj_divergence(self, inv_dt):
+        self._check(self.lib.sarasmg_proj_divergence(self.h, float(inv_dt)))
+
+    def proj_correct(self, dt):
+        self._check(self.lib.sarasmg_proj_correct(self.h, float(dt)))
+
+    def proj_step(self, dt):
+        hist, iters, cyc = self._hist()
+        self._check(self.lib.sarasmg_proj_step(self.h, float(dt), C.byref(cyc), _ptr(hist), iters.ctypes.data_as(C.POINTER(C.c_int))))
+        return dict(cycles=cyc.value, residuals=hist[:cyc.value].copy(), coarse_iters=iters[:cyc.value].copy())
 
     def last_rhs_mean(self):
         v = C.c_double(0.0)

@@ -18,6 +18,7 @@
 #include "gs_skew.cuh"
 #include "gs_strip.cuh"
 #include "mg_tma.cuh"
+#include "proj_kernels.cuh"
 
 #include <nccl.h>
 
@@ -160,6 +161,13 @@ struct sarasmg_solver_s {
     bool gs_legacy;             /* SARASMG_GS_LEGACY: one launch per hyperplane instead of the skewed single-launch sweep */
     cudaEvent_t user_ev[8];
     std::vector<std::pair<const void *, size_t>> pinned;   /* caller ranges this handle page-locked */
+    /* device-resident projection step: velocity components, pressure and the first-derivative metrics */
+    bool proj_ok;
+    ProjView pv;
+    double *d_vel[3];           /* Vx, Vy, Vz in their compact Blitz layouts */
+    size_t vel_elems[3];
+    double *d_presP;            /* P in the pitched level-0 layout */
+    double *d_pmet[6];          /* xi_xStaggr, et_yStaggr, zt_zStaggr, xi_xColloc, et_yColloc, zt_zColloc */
 };
 
 typedef sarasmg_solver_s S;
@@ -1435,6 +1443,9 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     s->prolong_legacy = getenv("SARASMG_PROLONG_LEGACY") != nullptr;
     s->coarsen_legacy = getenv("SARASMG_COARSEN_LEGACY") != nullptr;
     for (int q = 0; q < 8; q++) s->user_ev[q] = nullptr;
+    s->proj_ok = false; s->d_presP = nullptr;
+    for (int q = 0; q < 3; q++) { s->d_vel[q] = nullptr; s->vel_elems[q] = 0; }
+    for (int q = 0; q < 6; q++) s->d_pmet[q] = nullptr;
     memset(s->prof_ms, 0, sizeof(s->prof_ms));
     memset(s->prof_n, 0, sizeof(s->prof_n));
     for (int q = 0; q < 3; q++) s->d_wall[q] = nullptr;
@@ -1635,6 +1646,9 @@ int sarasmg_destroy(sarasmg_handle s) {
     cudaFree(s->d_part); cudaFree(s->d_scal); cudaFree(s->d_iters);
     cudaFreeHost(s->h_scal); cudaFreeHost(s->h_iters);
     cudaFree(s->d_in_p); cudaFree(s->d_in_rhs);
+    for (int q = 0; q < 3; q++) cudaFree(s->d_vel[q]);
+    for (int q = 0; q < 6; q++) cudaFree(s->d_pmet[q]);
+    cudaFree(s->d_presP);
     for (auto &e : s->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto &e : s->ev_pool) cudaEventDestroy(e);
     cudaEventDestroy(s->ev_solve0); cudaEventDestroy(s->ev_solve1);
@@ -1721,6 +1735,112 @@ int sarasmg_solve(sarasmg_handle s, double *p_inout, const double *rhs, int *cyc
     TRY(sarasmg_upload(s, p_inout, rhs));
     TRY(sarasmg_solve_resident(s, cycles_done, residual_history, coarse_iters));
     TRY(sarasmg_download(s, p_inout));
+    return 0;
+}
+
+/* ---- device-resident projection step ---- */
+int sarasmg_proj_setup(sarasmg_handle s, const sarasmg_proj_desc *d) {
+    if (!s || !d) return set_err("sarasmg_proj_setup: null argument");
+    if (s->planar) return set_err("sarasmg_proj_setup: the device-resident projection step is built for multigrid_d3 only");
+    if (s->d.n_proc != 1) return set_err("sarasmg_proj_setup: one rank only (Pp.syncData across ranks, mpidata.cc:278-306, is SURVEY row 8f-2)");
+    if (!d->xi_x_staggr || !d->et_y_staggr || !d->zt_z_staggr || !d->xi_x_colloc || !d->et_y_colloc || !d->zt_z_colloc)
+        return set_err("sarasmg_proj_setup: null metric array");
+    CU(cudaSetDevice(s->d.device));
+    TRY(ensure_inputs(s));
+    const LevelView &v0 = s->lev[0].v;
+    ProjView &V = s->pv;
+    V.nx = v0.nx; V.ny = v0.ny; V.nz = v0.nz;
+    V.dXi = d->d_xi; V.dEt = d->d_et; V.dZt = d->d_zt;
+    V.p2 = (is_pow2(V.dXi) && is_pow2(V.dEt) && is_pow2(V.dZt) && !s->no_pow2) ? 1 : 0;
+    V.rXi = 1.0 / V.dXi; V.rEt = 1.0 / V.dEt; V.rZt = 1.0 / V.dZt;
+    const double *src[6] = {d->xi_x_staggr, d->et_y_staggr, d->zt_z_staggr, d->xi_x_colloc, d->et_y_colloc, d->zt_z_colloc};
+    const int len[6] = {v0.nx + 2, v0.ny + 2, v0.nz + 2, v0.nx + 1, v0.ny + 1, v0.nz + 1};
+    for (int q = 0; q < 6; q++) {
+        if (!s->d_pmet[q]) CU(cudaMalloc(&s->d_pmet[q], sizeof(double) * len[q]));
+        CU(cudaMemcpyAsync(s->d_pmet[q], src[q], sizeof(double) * len[q], cudaMemcpyHostToDevice, s->st));
+    }
+    V.xs = s->d_pmet[0] + 1; V.ys = s->d_pmet[1] + 1; V.zs = s->d_pmet[2] + 1;
+    V.xc = s->d_pmet[3] + 1; V.yc = s->d_pmet[4] + 1; V.zc = s->d_pmet[5] + 1;
+    const size_t ve[3] = {(size_t)(v0.nx + 1) * (v0.ny + 2) * (v0.nz + 2), (size_t)(v0.nx + 2) * (v0.ny + 1) * (v0.nz + 2),
+                          (size_t)(v0.nx + 2) * (v0.ny + 2) * (v0.nz + 1)};
+    for (int q = 0; q < 3; q++) {
+        s->vel_elems[q] = ve[q];
+        if (!s->d_vel[q]) CU(cudaMalloc(&s->d_vel[q], sizeof(double) * ve[q]));
+        CU(cudaMemsetAsync(s->d_vel[q], 0, sizeof(double) * ve[q], s->st));
+    }
+    if (!s->d_presP) CU(cudaMalloc(&s->d_presP, s->lev[0].elems * sizeof(double)));
+    CU(cudaMemsetAsync(s->d_presP, 0, s->lev[0].elems * sizeof(double), s->st));
+    CU(cudaStreamSynchronize(s->st));
+    s->proj_ok = true;
+    return 0;
+}
+
+/* which: 0 Vx, 1 Vy, 2 Vz (compact Blitz layouts), 3 P, 4 Pp (the initial guess of the next solve): padded staggered arrays */
+int sarasmg_proj_upload(sarasmg_handle s, int which, const double *host) {
+    if (!s || !host || which < 0 || which > 4) return set_err("sarasmg_proj_upload: bad argument");
+    if (!s->proj_ok) return set_err("sarasmg_proj_upload: call sarasmg_proj_setup first");
+    CU(cudaSetDevice(s->d.device));
+    if (which < 3) CU(cudaMemcpyAsync(s->d_vel[which], host, sizeof(double) * s->vel_elems[which], cudaMemcpyHostToDevice, s->st));
+    else TRY(copy_h2d(s, s->lev[0], which == 3 ? s->d_presP : s->d_in_p, host));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+/* which: 0..4 as above, 5 mgRHS (the divergence / dt the last sarasmg_proj_divergence wrote) */
+int sarasmg_proj_download(sarasmg_handle s, int which, double *host) {
+    if (!s || !host || which < 0 || which > 5) return set_err("sarasmg_proj_download: bad argument");
+    if (!s->proj_ok) return set_err("sarasmg_proj_download: call sarasmg_proj_setup first");
+    CU(cudaSetDevice(s->d.device));
+    if (which < 3) CU(cudaMemcpyAsync(host, s->d_vel[which], sizeof(double) * s->vel_elems[which], cudaMemcpyDeviceToHost, s->st));
+    else TRY(copy_d2h(s, s->lev[0], host, which == 3 ? s->d_presP : (which == 4 ? s->d_in_p : s->d_in_rhs)));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+static int proj_divergence(S *s, double inv_dt) {
+    const LevelView &v0 = s->lev[0].v;
+    const dim3 grid(cdiv(v0.Fz, 128), v0.Fy, v0.Fx);
+    k_proj_divergence<<<grid, 128, 0, s->st>>>(s->d_vel[0], s->d_vel[1], s->d_vel[2], s->d_in_rhs, v0, s->pv, inv_dt);
+    return kcheck(s, "k_proj_divergence");
+}
+static int proj_correct(S *s, double dt) {
+    Level &L0 = s->lev[0];
+    const LevelView &v0 = L0.v;
+    /* inFn.F = pressureData(0) over the whole padded box (p:151): Pp, which is also the initial guess of the next solve */
+    k_copy_padded<<<std::min(cdiv((long long)v0.Fx * v0.Fy, 1), 148u * 8u), 256, 0, s->st>>>(L0.buf[SARASMG_PRESSURE], s->d_in_p, v0);
+    TRY(kcheck(s, "k_copy_padded"));
+    const int xper = (s->d.face_ranks[0] == s->d.rank) ? 1 : 0, yper = (s->d.face_ranks[2] == s->d.rank) ? 1 : 0;
+    if (xper || yper) {
+        k_proj_sync_faces<<<std::min(cdiv(2LL * v0.ny * v0.nz + 2LL * v0.nx * v0.nz, 256), 2048u), 256, 0, s->st>>>(s->d_in_p, v0, xper, yper);
+        TRY(kcheck(s, "k_proj_sync_faces"));
+    }
+    k_proj_sync_edges<<<cdiv(4LL * v0.nz, 256), 256, 0, s->st>>>(s->d_in_p, v0);
+    TRY(kcheck(s, "k_proj_sync_edges"));
+    const dim3 grid(cdiv(v0.Fz, 128), v0.Fy, v0.Fx);
+    k_proj_correct<<<grid, 128, 0, s->st>>>(s->d_in_p, s->d_presP, s->d_vel[0], s->d_vel[1], s->d_vel[2], v0, s->pv, dt);
+    return kcheck(s, "k_proj_correct");
+}
+
+int sarasmg_proj_divergence(sarasmg_handle s, double inv_dt) {
+    if (!s || !s->proj_ok) return set_err("sarasmg_proj_divergence: call sarasmg_proj_setup first");
+    CU(cudaSetDevice(s->d.device));
+    TRY(proj_divergence(s, inv_dt));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+int sarasmg_proj_correct(sarasmg_handle s, double dt) {
+    if (!s || !s->proj_ok) return set_err("sarasmg_proj_correct: call sarasmg_proj_setup first");
+    CU(cudaSetDevice(s->d.device));
+    TRY(proj_correct(s, dt));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+int sarasmg_proj_step(sarasmg_handle s, double dt, int *cycles_done, double *residual_history, int *coarse_iters) {
+    if (!s || !s->proj_ok) return set_err("sarasmg_proj_step: call sarasmg_proj_setup first");
+    CU(cudaSetDevice(s->d.device));
+    TRY(proj_divergence(s, 1.0 / dt));
+    TRY(solve_core(s, s->d_in_p, s->d_in_rhs, cycles_done, residual_history, coarse_iters));
+    TRY(proj_correct(s, dt));
+    CU(cudaStreamSynchronize(s->st));
     return 0;
 }
 
