@@ -200,6 +200,88 @@ __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_ca
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Peer-memory halo PUSH of the Jacobi sweep (several ranks, CUDA IPC over NVLink).                     */
+/* The sweep that computes a boundary plane also stores it into the neighbour's pad: every level array  */
+/* of a rank lives in one slab that its face neighbours map, the slabs have the same layout on every     */
+/* rank, so the neighbour's copy of the array being written is `its slab + the same offset`.  No pack,   */
+/* no unpack, no exchange launch: the last CTA of the sweep raises a flag in each neighbour's arena, and  */
+/* the face kernel that follows the sweep anyway (wall / periodic-z BCs of imposeBC) waits for the       */
+/* neighbours' flags before it reads a pad.  Why this is safe with the Jacobi ping-pong (A -> B, B -> A): */
+/* sweep n writes B's core here and B's pads at the neighbours, which nobody reads during sweep n; a      */
+/* neighbour starts sweep n+1 (which writes A's pads here) only after its face kernel has seen this       */
+/* rank's flag n, i.e. after this rank has finished reading A.  Only FACE pads are pushed (core rows of   */
+/* the plane): the four edge columns (x pad and y pad at once) are not, see op_smooth in sarasmg.cu.      */
+/* ------------------------------------------------------------------------------------------------ */
+/* Bounded spin: a neighbour that never signals (a rank died, or ranks disagree on the exchange count) must not hang the
+ * GPU.  After 2^27 polls (about a minute: ranks may legitimately be seconds apart) the waiter records the exchange
+ * number in *err and goes on; the host turns a non-zero *err into an error at the next synchronisation point. */
+__device__ __forceinline__ void ipc_wait_flag(const unsigned *flag, const unsigned epoch, unsigned *err) {
+    if (!flag) return;
+    if (err && *(volatile unsigned *)err) return;          /* an earlier wait already failed: do not stack timeouts */
+    unsigned v;
+    unsigned spins = 0;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - epoch) >= 0) return;
+        if ((spins & 1023u) == 1023u) __nanosleep(200);
+    } while (++spins < (1u << 27));
+    if (err) atomicMax(err, epoch | 0x80000000u);
+}
+__device__ __forceinline__ void ipc_signal(unsigned *flag, const unsigned epoch) {
+    if (flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+struct HaloPush {
+    double *dst[4];             /* the neighbour's copy of the array this sweep writes: left, right, front, back (nullptr: none) */
+    unsigned *sflag[4];         /* the flag to raise in that neighbour's arena */
+    const unsigned *base;       /* exchange number = *base + add (see IpcPlan) */
+    unsigned add;
+    unsigned *counter;          /* arrival counter of this rank */
+};
+struct HaloWait {
+    const unsigned *flag[4];    /* this rank's push flags, one per face (nullptr: nothing to wait for) */
+    const unsigned *base;
+    unsigned add;
+    unsigned *err;
+};
+/* Every CTA of a pushing sweep calls this once, by all its threads, after its last store.  One thread fences for the CTA
+ * (the barrier orders the other threads' stores before its fence, which is cumulative -- the grid.sync idiom): a
+ * system-scope fence per warp costs microseconds, and CTAs that stored nothing remote need none. */
+__device__ __forceinline__ void halo_push_signal(const HaloPush &H, const bool cta_pushed) {
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        if (cta_pushed) __threadfence_system();
+        const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned t = atomicAdd(H.counter, 1u);
+        if (t == nb - 1) {
+            *H.counter = 0u;
+            __threadfence_system();
+            const unsigned ep = *H.base + H.add;
+#pragma unroll
+            for (int f = 0; f < 4; f++) ipc_signal(H.sflag[f], ep);
+        }
+    }
+}
+__device__ __forceinline__ bool halo_cta_pushes(const HaloPush &H, const LevelView &L, const int i0, const int i1, const int j0, const int j1) {
+    return (H.dst[0] && i0 <= 1 && 1 < i1) || (H.dst[1] && i0 <= L.nx - 2 && L.nx - 2 < i1) ||
+           (H.dst[2] && j0 <= 1 && 1 < j1) || (H.dst[3] && j0 <= L.ny - 2 && L.ny - 2 < j1);
+}
+/* the (one or two) results of a thread's z pair at (i, j) go to the neighbours that own a pad there */
+__device__ __forceinline__ void halo_push_store(const HaloPush &H, const LevelView &L, const int i, const int j, const int k0,
+                                                const double2 v, const bool has2) {
+    const long long zc = k0 + 1 + MG_LEAD;
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+        if (!H.dst[f]) continue;
+        long long o;
+        if (f == 0) { if (i != 1) continue; o = (long long)(L.nx + 1) * L.plane + (long long)(j + 1) * L.pitch + zc; }
+        else if (f == 1) { if (i != L.nx - 2) continue; o = (long long)(j + 1) * L.pitch + zc; }
+        else if (f == 2) { if (j != 1) continue; o = (long long)(i + 1) * L.plane + (long long)(L.ny + 1) * L.pitch + zc; }
+        else { if (j != L.ny - 2) continue; o = (long long)(i + 1) * L.plane + zc; }
+        if (has2) *reinterpret_cast<double2 *>(H.dst[f] + o) = v; else H.dst[f][o] = v.x;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Jacobi sweep (d3:153-166, d2:131-140) and residual (d3:96-108, d2:95-103): x-marching kernels      */
 /* Thread = one aligned z pair (k0, k0+1) of row j; marches i over [i0, i1).                          */
 /* Algorithmic traffic: 24 B per core point (read p, read rhs, write out).                            */
@@ -220,10 +302,9 @@ __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<do
 #endif
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int DIM, int MODE /* 0 Jacobi, 1 residual */, bool XU /* MODE 0: xix2 constant on this level, the Jacobi diagonal is march-invariant;
-                                                                 MODE 1: the six divisors are powers of two (div_by) */>
-__global__ void __launch_bounds__(256, MG_MARCH_MINB)
-k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, double *__restrict__ O, const LevelView L,
-                const int ichunk) {
+                                                                 MODE 1: the six divisors are powers of two (div_by) */, bool PUSH>
+__device__ __forceinline__ void stencil_march_body(const double *__restrict__ P, const double *__restrict__ R, double *__restrict__ O,
+                                                   const LevelView &L, const int ichunk, const HaloPush *H) {
     const int k0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int j = (DIM == 3) ? (blockIdx.y * blockDim.y + threadIdx.y) : 0;
     if (k0 >= L.nz || j >= L.ny) return;
@@ -265,6 +346,7 @@ k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, doub
         rden_a = 1.0 / den_a; rden_b = 1.0 / den_b;
     }
 
+    const bool push_row = PUSH && ((H->dst[2] && j == 1) || (H->dst[3] && j == L.ny - 2));
     double2 pW = ld2(p + (long long)i0 * plane);          /* plane i0-1 */
     double2 pC = ld2(p + (long long)(i0 + 1) * plane);    /* plane i0   */
     for (int i = i0; i < i1; ++i) {
@@ -309,8 +391,24 @@ k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, doub
             }
         }
         if (has2) st2(o + b, out); else o[b] = out.x;
+        if (PUSH && (push_row | (i == 1) | (i == L.nx - 2))) halo_push_store(*H, L, i, j, k0, out, has2);
         pW = pC; pC = pE;
     }
+}
+template <int DIM, int MODE, bool XU>
+__global__ void __launch_bounds__(256, MG_MARCH_MINB)
+k_stencil_march(const double *__restrict__ P, const double *__restrict__ R, double *__restrict__ O, const LevelView L,
+                const int ichunk) {
+    stencil_march_body<DIM, MODE, XU, false>(P, R, O, L, ichunk, nullptr);
+}
+/* Jacobi sweep of a rank with neighbours: the same arithmetic, plus the halo push (3-D only) */
+template <bool XU>
+__global__ void __launch_bounds__(256, MG_MARCH_MINB)
+k_stencil_march_push(const double *__restrict__ P, const double *__restrict__ R, double *__restrict__ O, const LevelView L,
+                     const int ichunk, const HaloPush H) {
+    stencil_march_body<3, 0, XU, true>(P, R, O, L, ichunk, &H);
+    const int i0 = blockIdx.z * ichunk, j0 = blockIdx.y * blockDim.y;
+    halo_push_signal(H, halo_cta_pushes(H, L, i0, min(i0 + ichunk, L.nx), j0, j0 + (int)blockDim.y));
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -758,6 +856,17 @@ template <int DIM>
 __global__ void __launch_bounds__(256) k_faces(double *A, const LevelView L, const FaceModes F) {
     faces_apply<DIM>(A, L, F, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
+/* the face kernel after a pushing Jacobi sweep: wait for the neighbours' pushes (HaloPush), then the same face operations */
+template <int DIM>
+__global__ void __launch_bounds__(256) k_faces_wait(double *A, const LevelView L, const FaceModes F, const HaloWait W) {
+    if (threadIdx.x == 0) {
+        const unsigned ep = *W.base + W.add;
+#pragma unroll
+        for (int f = 0; f < 4; f++) ipc_wait_flag(W.flag[f], ep, W.err);
+    }
+    __syncthreads();
+    faces_apply<DIM>(A, L, F, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
 
 /* y-row pack/unpack for the inter-GPU halo (MPI_Type_vector of d3:492-497): row j of every x plane <-> contiguous buffer */
 __global__ void __launch_bounds__(256) k_pack_y(const double *__restrict__ A, const LevelView L, const int j, double *__restrict__ buf) {
@@ -858,33 +967,13 @@ __global__ void __launch_bounds__(256) k_unpack_y2(double *__restrict__ A, const
 /* overwrites a slot I have not consumed.  Data stores are made visible with __threadfence_system() before   */
 /* the last CTA of the grid raises the remote flags; consumers read the buffers with L1-bypassing loads.     */
 /* ------------------------------------------------------------------------------------------------ */
-/* Bounded spin: a neighbour that never signals (a rank died, or ranks disagree on the exchange count) must not hang the
- * GPU.  After 2^27 polls (about a minute: ranks may legitimately be seconds apart) the waiter records the exchange
- * number in *err and goes on; the host turns a non-zero *err into an error at the next synchronisation point. */
-__device__ __forceinline__ void ipc_wait_flag(const unsigned *flag, const unsigned epoch, unsigned *err) {
-    if (!flag) return;
-    if (err && *(volatile unsigned *)err) return;          /* an earlier wait already failed: do not stack timeouts */
-    unsigned v;
-    unsigned spins = 0;
-    do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if ((int)(v - epoch) >= 0) return;
-        if ((spins & 1023u) == 1023u) __nanosleep(200);
-    } while (++spins < (1u << 27));
-    if (err) atomicMax(err, epoch | 0x80000000u);
-}
-__device__ __forceinline__ void ipc_signal(unsigned *flag, const unsigned epoch) {
-    if (flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-}
 /* every CTA calls this after its stores; the last one to arrive raises the flags */
 __device__ __forceinline__ void ipc_last_cta_signals(unsigned *counter, unsigned *flag_a, unsigned *flag_b, const unsigned epoch) {
-    __shared__ bool last;
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();         /* one fence per CTA: cumulative over the stores the barrier ordered before it */
         const unsigned t = atomicAdd(counter, 1u);
-        last = (t == gridDim.x - 1);
-        if (last) { *counter = 0u; __threadfence_system(); ipc_signal(flag_a, epoch); ipc_signal(flag_b, epoch); }
+        if (t == gridDim.x - 1) { *counter = 0u; __threadfence_system(); ipc_signal(flag_a, epoch); ipc_signal(flag_b, epoch); }
     }
 }
 __device__ __forceinline__ double ld_cg_f64(const double *p) { return __ldcg(p); }
@@ -995,9 +1084,8 @@ __global__ void __launch_bounds__(1024) k_ipc_exchange_cta(double *A, const Leve
             if (send[0]) send[0][q] = A[mg_at(L, 1, j, k)];
             if (send[1]) send[1][q] = A[mg_at(L, L.nx - 2, j, k)];
         }
-        __threadfence_system();
         __syncthreads();
-        if (tid == 0) { ipc_signal(sflag[0], epoch); ipc_signal(sflag[1], epoch); }
+        if (tid == 0) { __threadfence_system(); ipc_signal(sflag[0], epoch); ipc_signal(sflag[1], epoch); }
     }
     if (tid == 0) { ipc_wait_flag(rflag[0], epoch, P.err); ipc_wait_flag(rflag[1], epoch, P.err); }
     __syncthreads();
@@ -1016,9 +1104,8 @@ __global__ void __launch_bounds__(1024) k_ipc_exchange_cta(double *A, const Leve
                 if (send[2]) send[2][q] = A[mg_at(L, i, 1, k)];
                 if (send[3]) send[3][q] = A[mg_at(L, i, L.ny - 2, k)];
             }
-            __threadfence_system();
             __syncthreads();
-            if (tid == 0) { ipc_signal(sflag[2], epoch); ipc_signal(sflag[3], epoch); }
+            if (tid == 0) { __threadfence_system(); ipc_signal(sflag[2], epoch); ipc_signal(sflag[3], epoch); }
         }
         if (tid == 0) { ipc_wait_flag(rflag[2], epoch, P.err); ipc_wait_flag(rflag[3], epoch, P.err); }
         __syncthreads();

@@ -120,11 +120,10 @@ __device__ __forceinline__ void tma_point_pair(const TmaRow &r, const double2 pE
     }
 }
 
-template <int MODE, bool FAST>
-__global__ void __launch_bounds__(MG_TMA_WARPS * 32, 2)
-k_stencil_tma(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapR, double *__restrict__ O,
-              const LevelView L, const int ichunk, const int norm_order, const double hx_c, const double hy_c, const double hz_c,
-              double *__restrict__ part, const int nblocks) {
+template <int MODE, bool FAST, bool PUSH>
+__device__ __forceinline__ void stencil_tma_body(const CUtensorMap *mapP, const CUtensorMap *mapR, double *__restrict__ O,
+                                                 const LevelView &L, const int ichunk, const int norm_order, const double hx_c, const double hy_c,
+                                                 const double hz_c, double *__restrict__ part, const int nblocks, const HaloPush *H) {
     extern __shared__ __align__(128) double tma_ring[];
     __shared__ __align__(8) uint64_t bars[2 * MG_TMA_STAGES];       /* full[0..S), empty[S..2S) */
     __shared__ __align__(16) double2 xt[MG_TMA_MAXCH];              /* per x-plane coefficient pair of this chunk */
@@ -159,8 +158,8 @@ k_stencil_tma(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ 
         const uint32_t st = ring + s * MG_TMA_STAGE_BYTES, bar = bar0 + 8 * s;
         const bool with_r = (n >= 1 && n <= nplanes - 2);
         mbar_expect_tx(bar, MG_TMA_P_BYTES + (with_r ? MG_TMA_R_BYTES : 0));
-        tma_load_3d(st, &mapP, bar, k_t + 2, j_t, i0 + n);                       /* (k_t-2)+4, (j_t-1)+1, (i0-1+n)+1 */
-        if (with_r) tma_load_3d(st + MG_TMA_P_SLOT, &mapR, bar, k_t + 4, j_t + 1, i0 + n);
+        tma_load_3d(st, mapP, bar, k_t + 2, j_t, i0 + n);                       /* (k_t-2)+4, (j_t-1)+1, (i0-1+n)+1 */
+        if (with_r) tma_load_3d(st + MG_TMA_P_SLOT, mapR, bar, k_t + 4, j_t + 1, i0 + n);
     };
     if (producer)
         for (int n = 0; n < MG_TMA_STAGES && n < nplanes; n++) issue(n, n);
@@ -195,6 +194,14 @@ k_stencil_tma(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ 
     const long long plane = L.plane;
     const int pitch = L.pitch;
     double num = 0.0, den = 0.0;
+    /* halo push (PUSH): loop iterations n whose x plane is a neighbour's pad, and whether one of this thread's rows is */
+    int push_n0 = -1, push_n1 = -1;
+    bool push_rows = false;
+    if (PUSH) {
+        if (H->dst[0]) push_n0 = 2 - i0;                    /* plane i = 1 is iteration n = i - i0 + 1 */
+        if (H->dst[1]) push_n1 = L.nx - 1 - i0;             /* plane i = nx - 2 */
+        push_rows = (H->dst[2] && (ja == 1 || ja + 1 == 1)) || (H->dst[3] && (ja == L.ny - 2 || ja + 1 == L.ny - 2));
+    }
 
     /* prologue: own pairs of planes i0-1 (n = 0) and i0 (n = 1); stage 0 is released right away */
     mbar_wait(bar0, 0);
@@ -235,6 +242,10 @@ k_stencil_tma(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ 
                                            z2a, z2b, z1a, z1b, dv, has2, norm_order, obv, num, den);
                 if (MODE != 2) { if (has2) st2(ob + pitch, obv); else ob[pitch] = obv.x; }
             }
+            if (PUSH && (push_rows | (n == push_n0) | (n == push_n1))) {         /* rare; kept out of the way: the loop is issue-bound */
+                halo_push_store(*H, L, i0 + n - 1, ja, k0, oa, has2);
+                if (act_b) halo_push_store(*H, L, i0 + n - 1, ja + 1, k0, obv, has2);
+            }
         }
         ra.pW = ra.pC; ra.pC = pEa;
         rb.pW = rb.pC; rb.pC = pEb;
@@ -254,4 +265,21 @@ k_stencil_tma(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ 
         const double d2 = block_reduce<false>(den, red_sm);
         if (tx == 0 && ty == 0) { part[bid] = n2; part[nblocks + bid] = d2; }
     }
+}
+
+template <int MODE, bool FAST>
+__global__ void __launch_bounds__(MG_TMA_WARPS * 32, 2)
+k_stencil_tma(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapR, double *__restrict__ O,
+              const LevelView L, const int ichunk, const int norm_order, const double hx_c, const double hy_c, const double hz_c,
+              double *__restrict__ part, const int nblocks) {
+    stencil_tma_body<MODE, FAST, false>(&mapP, &mapR, O, L, ichunk, norm_order, hx_c, hy_c, hz_c, part, nblocks, nullptr);
+}
+/* Jacobi sweep of a rank with neighbours: the same arithmetic plus the halo push (mg_kernels.cuh, HaloPush) */
+template <bool FAST>
+__global__ void __launch_bounds__(MG_TMA_WARPS * 32, 2)
+k_stencil_tma_push(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapR, double *__restrict__ O,
+                   const LevelView L, const int ichunk, const HaloPush H) {
+    stencil_tma_body<0, FAST, true>(&mapP, &mapR, O, L, ichunk, 0, 0.0, 0.0, 0.0, nullptr, 0, &H);
+    const int i0 = blockIdx.z * ichunk, j0 = blockIdx.y * MG_TMA_TY;
+    halo_push_signal(H, halo_cta_pushes(H, L, i0, min(i0 + ichunk, L.nx), j0, j0 + MG_TMA_TY));
 }

@@ -74,7 +74,9 @@ struct Level {
     double *gss_rden, *gss_xpair;
     size_t gss_smem;
     bool gss_ok;
-    double *buf[3];         /* SARASMG_PRESSURE, SARASMG_RESIDUAL, SARASMG_TMP */
+    double *buf[3];         /* SARASMG_PRESSURE, SARASMG_RESIDUAL, SARASMG_TMP: carved out of the solver's one slab */
+    size_t off[3];          /* their offsets (doubles) in the slab: the same on every rank, so a neighbour's copy of an array
+                               is its mapped slab + off; swapped together with buf[] */
     CUtensorMap tmapP[3];   /* TMA descriptors of the three arrays for the pressure box (with halo ring) ... */
     CUtensorMap tmapR[3];   /* ... and for the right-hand-side box; swapped together with buf[] */
     bool tma;               /* level is large enough for k_stencil_tma and the descriptors exist */
@@ -121,8 +123,16 @@ struct sarasmg_solver_s {
     double *ipc_arena;
     size_t ipc_slot, ipc_xc, ipc_yc;        /* doubles per parity slot; level-0 x / y face counts (fix the layout of a slot) */
     double *ipc_peer[4];                    /* mapped arena of the left / right / front / back neighbour (nullptr: none) */
-    void *ipc_opened[4];
+    void *ipc_opened[8];
     int ipc_nopened;
+    double *slab;                           /* every level array of this rank: ONE allocation, so one IPC handle maps all of it */
+    size_t slab_elems;
+    double *slab_peer[4];                   /* the face neighbours' slabs (peer-memory halo push of the Jacobi sweeps) */
+    bool push_ok;                           /* the neighbours' slabs are mapped: Jacobi sweeps may store their boundary planes straight into them */
+    bool push_on;                           /* inside a V-cycle of mgSolve: intermediate edge pads may stay stale (see op_smooth) */
+    bool pads_stale;                        /* level 0's edge pads are behind its core: finalize_pads before the array leaves the solver */
+    bool level_zero[32];                    /* pressureData(level) was just set to 0 (p:258) and nothing has written it since */
+    unsigned push_add[32];                  /* per level: exchange number (relative to *d_ipc_base) of the push the pads are waiting for; 0 = none */
     unsigned ipc_epoch;                     /* number of the last exchange (dense, the same on every rank) */
     unsigned *d_ipc_base;                   /* device word the exchange kernels add their position to (see IpcPlan) */
     unsigned ipc_base_h;                    /* its current value */
@@ -454,7 +464,65 @@ static void bc_modes(const S *s, int m[6]) {
     else { m[4] = wall; m[5] = wall; }
 }
 
+/* Peer-memory halo PUSH (mg_kernels.cuh, HaloPush).  Inside the V-cycles of mgSolve the Jacobi sweep of a rank with
+ * neighbours stores its boundary planes straight into the neighbours' pads, and the imposeBC after it (d3:575-668) only
+ * waits for their flags before it applies the wall / periodic-z / self-periodic face operations: no pack, exchange or unpack
+ * launches.  A push fills the FACE pads only.  The four edge columns (x pad and y pad at once), which updatePads' x-then-y
+ * order fills with the diagonal neighbour's values, keep older data: no 7-point operator reads them; the one reader of
+ * edge pads is the 27-point restriction of tmpDataArray, whose exchange stays the full one; and the pads mgSolve hands
+ * back (p:151) are rebuilt by one full imposeBC at the end of the solve (finalize_pads) -- imposeBC is a function of the
+ * core values only, so that reproduces the reference's last imposeBC exactly. */
+static bool push_level_ok(const S *s, int level) {
+    if (!s->push_on || !s->push_ok || s->d.gs_smooth || s->planar || level >= 32) return false;
+    if (s->d.test_poisson && !s->zeroBC) return false;      /* Dirichlet ghost values: the two-launch wall path stays */
+    const int me = s->d.rank;
+    const int *fr = s->d.face_ranks;
+    for (int f = 0; f < 4; f++) if (fr[f] != SARASMG_PROC_NULL && fr[f] != me) return true;
+    return false;
+}
+static unsigned next_exchange_number(S *s) { return s->capturing ? ++s->cap_sites : (++s->ipc_epoch - s->ipc_base_h); }
+static unsigned *my_ipc_flags(const S *s) { return (unsigned *)(s->ipc_arena + 2 * s->ipc_slot); }
+enum { IPC_PUSH_FLAG0 = 32, IPC_PUSH_COUNTER = 40 };        /* words of the arena's flag block used by the push (0..17: exchange kernels) */
+static HaloPush make_halo_push(S *s, const Level &L, int which) {
+    HaloPush H;
+    const int me = s->d.rank;
+    const int *fr = s->d.face_ranks;
+    const int opposite[4] = {1, 0, 3, 2};           /* my left plane is the neighbour's RIGHT pad, ... */
+    for (int f = 0; f < 4; f++) {
+        const bool rem = fr[f] != SARASMG_PROC_NULL && fr[f] != me;
+        H.dst[f] = rem ? s->slab_peer[f] + L.off[which] : nullptr;
+        H.sflag[f] = rem ? (unsigned *)(s->ipc_peer[f] + 2 * s->ipc_slot) + IPC_PUSH_FLAG0 + opposite[f] : nullptr;
+    }
+    H.base = s->d_ipc_base;
+    H.add = next_exchange_number(s);
+    H.counter = my_ipc_flags(s) + IPC_PUSH_COUNTER;
+    return H;
+}
+/* imposeBC after a pushing sweep: one face launch that first waits for the neighbours' pushes */
+static int impose_bc_pushed(S *s, int level) {
+    const Level &L = s->lev[level];
+    int m[6];
+    bc_modes(s, m);
+    const PadPlan pp = pad_plan(s);
+    FaceModes F;
+    for (int q = 0; q < 6; q++) F.m[q] = (m[q] != FACE_NONE) ? m[q] : pp.self[q];
+    F.xwall = F.ywall = F.zwall = nullptr;
+    HaloWait W;
+    const bool rem[4] = {pp.rl, pp.rr, pp.rf, pp.rb};
+    for (int f = 0; f < 4; f++) W.flag[f] = rem[f] ? my_ipc_flags(s) + IPC_PUSH_FLAG0 + f : nullptr;
+    W.base = s->d_ipc_base;
+    W.add = s->push_add[level];
+    W.err = s->d_ipc_base + 1;
+    s->push_add[level] = 0;
+    ProfScope ps(s, SARASMG_K_BC, level);
+    const LevelView &v = L.v;
+    const long long cnt = (long long)v.Fx * v.Fy + (long long)v.Fx * v.Fz + (long long)v.Fy * v.Fz;
+    k_faces_wait<3><<<face_blocks(cnt), 256, 0, s->st>>>(L.buf[SARASMG_PRESSURE], v, F, W);
+    return kcheck(s, "k_faces_wait");
+}
+
 static int impose_bc(S *s, int level) {
+    if (level < 32 && s->push_add[level]) return impose_bc_pushed(s, level);
     const Level &L = s->lev[level];
     double *P = L.buf[SARASMG_PRESSURE];
     int m[6];
@@ -745,9 +813,14 @@ static int gs_sweep(S *s, int level) {
 static int op_smooth(S *s, int count) {
     const int l = s->vLevel;
     Level &L = s->lev[l];
+    /* pressureData(l) == 0 everywhere, pads included (the memset of p:258 just ran): with homogeneous mirror / periodic faces
+     * the first imposeBC copies zeros onto zeros on every rank -- skipped.  (Not under TEST_POISSON, whose odd mirror
+     * would write -0.0.) */
+    const bool skip_first_bc = l < 32 && s->level_zero[l] && s->zeroBC && !s->d.test_poisson && count > 0;
+    if (l < 32) s->level_zero[l] = false;
     for (int n = 0; n < count; ++n) {
         s->bucket = 2;
-        TRY(impose_bc(s, l));
+        if (!(n == 0 && skip_first_bc)) TRY(impose_bc(s, l));
         s->bucket = 1;
         {
             ProfScope ps(s, SARASMG_K_SMOOTH, l);
@@ -756,7 +829,20 @@ static int op_smooth(S *s, int count) {
             } else {
                 const MarchGeom g = march_geom(s, L.v);
                 double *P = L.buf[SARASMG_PRESSURE], *R = L.buf[SARASMG_RESIDUAL], *T = L.buf[SARASMG_TMP];
-                if (L.tma) {
+                if (push_level_ok(s, l)) {
+                    /* rank with neighbours, inside mgSolve: the sweep stores its boundary planes into the neighbours' pads */
+                    const HaloPush H = make_halo_push(s, L, SARASMG_TMP);
+                    s->push_add[l] = H.add;
+                    if (l == 0) s->pads_stale = true;
+                    if (L.tma) {
+                        const TmaGeom t = tma_geom(L.v);
+                        if (L.x_uniform) k_stencil_tma_push<true><<<t.grid, t.block, MG_TMA_SMEM, s->st>>>(L.tmapP[SARASMG_PRESSURE], L.tmapR[SARASMG_RESIDUAL], T, L.v, t.ichunk, H);
+                        else k_stencil_tma_push<false><<<t.grid, t.block, MG_TMA_SMEM, s->st>>>(L.tmapP[SARASMG_PRESSURE], L.tmapR[SARASMG_RESIDUAL], T, L.v, t.ichunk, H);
+                    } else {
+                        if (L.x_uniform) k_stencil_march_push<true><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk, H);
+                        else k_stencil_march_push<false><<<g.grid, g.block, 0, s->st>>>(P, R, T, L.v, g.ichunk, H);
+                    }
+                } else if (L.tma) {
                     const TmaGeom t = tma_geom(L.v);
                     if (L.x_uniform) k_stencil_tma<0, true><<<t.grid, t.block, MG_TMA_SMEM, s->st>>>(L.tmapP[SARASMG_PRESSURE], L.tmapR[SARASMG_RESIDUAL], T, L.v, t.ichunk, 0, 0.0, 0.0, 0.0, nullptr, 0);
                     else k_stencil_tma<0, false><<<t.grid, t.block, MG_TMA_SMEM, s->st>>>(L.tmapP[SARASMG_PRESSURE], L.tmapR[SARASMG_RESIDUAL], T, L.v, t.ichunk, 0, 0.0, 0.0, 0.0, nullptr, 0);
@@ -769,6 +855,7 @@ static int op_smooth(S *s, int count) {
                 }
                 TRY(kcheck(s, "k_stencil_march<jacobi>"));
                 std::swap(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_TMP]);      /* d3:168 */
+                std::swap(L.off[SARASMG_PRESSURE], L.off[SARASMG_TMP]);
                 std::swap(L.tmapP[SARASMG_PRESSURE], L.tmapP[SARASMG_TMP]);
                 std::swap(L.tmapR[SARASMG_PRESSURE], L.tmapR[SARASMG_TMP]);
             }
@@ -973,8 +1060,11 @@ static int setup_ipc_halo(S *s) {
     s->ipc_slot = 2 * s->ipc_xc + 2 * s->ipc_yc;
     const size_t arena_bytes = (2 * s->ipc_slot + 64) * sizeof(double);
     int ok = want ? 1 : 0;
-    cudaIpcMemHandle_t mine;
+    /* the halo push of the Jacobi sweeps additionally needs the neighbours' level slabs (SARASMG_NO_PUSH: keep the exchange kernels) */
+    int okp = (want && !s->planar && !getenv("SARASMG_NO_PUSH")) ? 1 : 0;
+    cudaIpcMemHandle_t mine, mine_slab;
     memset(&mine, 0, sizeof(mine));
+    memset(&mine_slab, 0, sizeof(mine_slab));
     if (ok) {
         if (cudaMalloc(&s->ipc_arena, arena_bytes) != cudaSuccess) { cudaGetLastError(); s->ipc_arena = nullptr; ok = 0; }
         else {
@@ -982,11 +1072,15 @@ static int setup_ipc_halo(S *s) {
             if (cudaIpcGetMemHandle(&mine, s->ipc_arena) != cudaSuccess) { cudaGetLastError(); ok = 0; }
         }
     }
-    /* all-gather {handle, ok} */
-    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    if (ok && okp && cudaIpcGetMemHandle(&mine_slab, s->slab) != cudaSuccess) { cudaGetLastError(); okp = 0; }
+    if (!ok) okp = 0;
+    /* all-gather {arena handle, slab handle, ok, ok_push} */
+    const size_t rec = 2 * sizeof(cudaIpcMemHandle_t) + 8;
     std::vector<unsigned char> hmine(rec, 0), hall(rec * np, 0);
     memcpy(hmine.data(), &mine, sizeof(mine));
-    hmine[sizeof(mine)] = (unsigned char)ok;
+    memcpy(hmine.data() + sizeof(mine), &mine_slab, sizeof(mine_slab));
+    hmine[2 * sizeof(mine)] = (unsigned char)ok;
+    hmine[2 * sizeof(mine) + 1] = (unsigned char)okp;
     unsigned char *dm = nullptr, *da = nullptr;
     CU(cudaMalloc(&dm, rec));
     CU(cudaMalloc(&da, rec * np));
@@ -994,12 +1088,12 @@ static int setup_ipc_halo(S *s) {
     NC(ncclAllGather(dm, da, rec, ncclUint8, s->comm, s->st));
     CU(cudaMemcpyAsync(hall.data(), da, rec * np, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
-    for (int r = 0; r < np; r++) ok = ok && hall[r * rec + sizeof(mine)];
+    for (int r = 0; r < np; r++) { ok = ok && hall[r * rec + 2 * sizeof(mine)]; okp = okp && hall[r * rec + 2 * sizeof(mine) + 1]; }
     if (ok) {
         for (int f = 0; f < 4; f++) {
             const int r = d.face_ranks[f];
             if (r == SARASMG_PROC_NULL || r == d.rank || (s->planar && f >= 2)) continue;
-            for (int g = 0; g < f; g++) if (d.face_ranks[g] == r && s->ipc_peer[g]) s->ipc_peer[f] = s->ipc_peer[g];   /* same peer on two sides */
+            for (int g = 0; g < f; g++) if (d.face_ranks[g] == r && s->ipc_peer[g]) { s->ipc_peer[f] = s->ipc_peer[g]; s->slab_peer[f] = s->slab_peer[g]; }   /* same peer on two sides */
             if (s->ipc_peer[f]) continue;
             cudaIpcMemHandle_t h;
             memcpy(&h, hall.data() + r * rec, sizeof(h));
@@ -1007,16 +1101,26 @@ static int setup_ipc_halo(S *s) {
             if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
             s->ipc_opened[s->ipc_nopened++] = ptr;
             s->ipc_peer[f] = (double *)ptr;
+            if (okp) {
+                memcpy(&h, hall.data() + r * rec + sizeof(h), sizeof(h));
+                ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); okp = 0; }
+                else { s->ipc_opened[s->ipc_nopened++] = ptr; s->slab_peer[f] = (double *)ptr; }
+            }
         }
     }
+    if (!ok) okp = 0;
     /* agree: MIN over ranks of the final status (reuses the small device buffers) */
     int *di = (int *)dm;
-    CU(cudaMemcpyAsync(di, &ok, sizeof(int), cudaMemcpyHostToDevice, s->st));
-    NC(ncclAllReduce(di, di, 1, ncclInt, ncclMin, s->comm, s->st));
-    CU(cudaMemcpyAsync(&ok, di, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    int st2[2] = {ok, okp};
+    CU(cudaMemcpyAsync(di, st2, 2 * sizeof(int), cudaMemcpyHostToDevice, s->st));
+    NC(ncclAllReduce(di, di, 2, ncclInt, ncclMin, s->comm, s->st));
+    CU(cudaMemcpyAsync(st2, di, 2 * sizeof(int), cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
+    ok = st2[0]; okp = st2[1];
     CU(cudaFree(dm)); CU(cudaFree(da));
     s->ipc_ok = (ok != 0);
+    s->push_ok = (ok != 0 && okp != 0);
     if (!s->ipc_ok && want && d.rank == 0 && getenv("SARASMG_VERBOSE"))
         fprintf(stderr, "saras-mg: CUDA IPC halo buffers unavailable, using ncclSend/ncclRecv\n");
     return 0;
@@ -1196,7 +1300,26 @@ static int op_solve_coarsest(S *s, int *iters, bool sync) {
 }
 
 /* vCycle (p:219-280) */
+static int op_vcycle_body(S *s);
 static int op_vcycle(S *s, int *coarse_iters) {
+    (void)coarse_iters;
+    s->push_on = s->push_ok;            /* halo push of the Jacobi sweeps: inside V-cycles only (see push_level_ok) */
+    const int rc = op_vcycle_body(s);
+    s->push_on = false;
+    memset(s->level_zero, 0, sizeof(s->level_zero));
+    return rc;
+}
+/* after V-cycles that pushed halos: one full imposeBC on level 0 restores the edge pads of the array mgSolve hands back */
+static int finalize_pads(S *s) {
+    if (!s->pads_stale) return 0;
+    s->pads_stale = false;
+    const int lv = s->vLevel, zb = s->zeroBC;
+    s->vLevel = 0; s->zeroBC = 0;
+    const int rc = impose_bc(s, 0);
+    s->vLevel = lv; s->zeroBC = zb;
+    return rc;
+}
+static int op_vcycle_body(S *s) {
     const int D = s->D;
     s->vLevel = 0;
     s->zeroBC = 0;
@@ -1210,6 +1333,7 @@ static int op_vcycle(S *s, int *coarse_iters) {
             Level &L = s->lev[s->vLevel];
             ProfScope ps(s, SARASMG_K_MISC, s->vLevel);
             CU(cudaMemsetAsync(L.buf[SARASMG_PRESSURE], 0, L.elems * sizeof(double), s->st));
+            if (s->vLevel < 32 && s->vLevel != D) s->level_zero[s->vLevel] = true;
         }
         if (s->vLevel == D) TRY(op_solve_coarsest(s, nullptr, false));
         else TRY(op_smooth(s, s->d.pre_smooth));
@@ -1219,7 +1343,6 @@ static int op_vcycle(S *s, int *coarse_iters) {
         s->zeroBC = (s->vLevel == 0) ? 0 : 1;
         TRY(op_smooth(s, s->d.post_smooth));
     }
-    (void)coarse_iters;
     return 0;
 }
 
@@ -1281,6 +1404,7 @@ static int run_vcycle(S *s) {
             for (int l = 0; l < s->D; l++) {
                 Level &L = s->lev[l];
                 std::swap(L.buf[SARASMG_PRESSURE], L.buf[SARASMG_TMP]);
+                std::swap(L.off[SARASMG_PRESSURE], L.off[SARASMG_TMP]);
                 std::swap(L.tmapP[SARASMG_PRESSURE], L.tmapP[SARASMG_TMP]);
                 std::swap(L.tmapR[SARASMG_PRESSURE], L.tmapR[SARASMG_TMP]);
             }
@@ -1369,6 +1493,7 @@ static int solve_core(S *s, const double *in_p, const double *in_rhs, int *cycle
             prevResidual = mgResidual;
         }
     }
+    TRY(finalize_pads(s));
     CU(cudaEventRecord(s->ev_solve1, s->st));
     CU(cudaEventSynchronize(s->ev_solve1));
     float ms = 0.f;
@@ -1457,7 +1582,11 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     s->d_ipc_base = nullptr; s->ipc_base_h = 0;
     s->ipc_cta_max = getenv("SARASMG_IPC_CTA_MAX") ? atoll(getenv("SARASMG_IPC_CTA_MAX")) : 4096;
     s->ipc_ok = false; s->ipc_arena = nullptr; s->ipc_nopened = 0; s->ipc_epoch = 0;
-    for (int q = 0; q < 4; q++) { s->ipc_peer[q] = nullptr; s->ipc_opened[q] = nullptr; }
+    for (int q = 0; q < 4; q++) { s->ipc_peer[q] = nullptr; s->slab_peer[q] = nullptr; }
+    for (int q = 0; q < 8; q++) s->ipc_opened[q] = nullptr;
+    s->slab = nullptr; s->slab_elems = 0; s->push_ok = false; s->push_on = false; s->pads_stale = false;
+    memset(s->push_add, 0, sizeof(s->push_add));
+    memset(s->level_zero, 0, sizeof(s->level_zero));
     s->agg_P = s->agg_R = nullptr; s->agg_tab = nullptr; s->agg_met = nullptr; s->agg_ok = false;
     s->coarse_legacy = getenv("SARASMG_COARSE_LEGACY") != nullptr;
     s->coarse_global = getenv("SARASMG_COARSE_GLOBAL") != nullptr;
@@ -1468,6 +1597,20 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     const int D = s->D;
     s->lev.resize(D + 1);
     size_t moff[3] = {0, 0, 0};
+    {   /* one slab for the three arrays of every level (sizes as computed per level below) */
+        size_t tot = 0;
+        for (int l = 0; l <= D; l++) {
+            long long F[3];
+            for (int dd = 0; dd < 3; dd++) F[dd] = (s->planar && dd == 1) ? 3 : (((desc->n0[dd] - 1) >> l) + 1) + 2;
+            const long long pitch = ((F[2] - 2 + 6 + 3) / 4) * 4;
+            const size_t elems = (((size_t)F[0] * F[1] * pitch + 16 + 31) / 32) * 32;
+            tot += 3 * elems;
+        }
+        s->slab_elems = tot;
+        CU(cudaMalloc(&s->slab, tot * sizeof(double)));
+        CU(cudaMemsetAsync(s->slab, 0, tot * sizeof(double), s->st));
+    }
+    size_t slab_used = 0;
     for (int l = 0; l <= D; l++) {
         Level &L = s->lev[l];
         LevelView &v = L.v;
@@ -1483,10 +1626,12 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
         v.Fx = n[0] + 2; v.Fy = n[1] + 2; v.Fz = n[2] + 2;
         v.pitch = ((v.nz + 6 + 3) / 4) * 4;
         v.plane = (long long)v.Fy * v.pitch;
-        L.elems = (size_t)v.Fx * v.plane + 16;
+        L.elems = (((size_t)v.Fx * v.plane + 16 + 31) / 32) * 32;      /* multiple of 256 bytes: every array starts 256-byte aligned */
         for (int a = 0; a < 3; a++) {
-            CU(cudaMalloc(&L.buf[a], L.elems * sizeof(double)));
-            CU(cudaMemsetAsync(L.buf[a], 0, L.elems * sizeof(double), s->st));
+            if (slab_used + L.elems > s->slab_elems) return set_err("sarasmg_create: level slab layout mismatch");
+            L.off[a] = slab_used;
+            L.buf[a] = s->slab + slab_used;
+            slab_used += L.elems;
         }
         v.hx = desc->hx ? desc->hx[l] : 0.0;   v.hy = desc->hy ? desc->hy[l] : 0.0;   v.hz = desc->hz ? desc->hz[l] : 0.0;
         v.hx2 = desc->hx2 ? desc->hx2[l] : 0.0; v.hz2 = desc->hz2 ? desc->hz2[l] : 0.0; v.hzhx = desc->hzhx ? desc->hzhx[l] : 0.0;
@@ -1529,6 +1674,8 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     CU(cudaFuncSetAttribute(k_coarse_solve_smem<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_stencil_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
     CU(cudaFuncSetAttribute(k_stencil_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
+    CU(cudaFuncSetAttribute(k_stencil_tma_push<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
+    CU(cudaFuncSetAttribute(k_stencil_tma_push<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
     CU(cudaFuncSetAttribute(k_stencil_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
     CU(cudaFuncSetAttribute(k_stencil_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
     CU(cudaFuncSetAttribute(k_stencil_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
@@ -1631,7 +1778,6 @@ int sarasmg_destroy(sarasmg_handle s) {
     s->graphs.clear();
     if (s->has_comm) ncclCommDestroy(s->comm);
     for (auto &L : s->lev) {
-        for (int a = 0; a < 3; a++) cudaFree(L.buf[a]);
         for (int m = 0; m < 6; m++) cudaFree(L.met[m]);
         cudaFree(L.gs_tasks); cudaFree(L.gs_sync);
         cudaFree(L.gss_tasks); cudaFree(L.gss_sync); cudaFree(L.gss_rden); cudaFree(L.gss_xpair);
@@ -1642,6 +1788,7 @@ int sarasmg_destroy(sarasmg_handle s) {
     cudaFree(s->d_ipc_base);
     for (int q = 0; q < s->ipc_nopened; q++) cudaIpcCloseMemHandle(s->ipc_opened[q]);
     cudaFree(s->ipc_arena);
+    cudaFree(s->slab);
     cudaFree(s->agg_P); cudaFree(s->agg_R); cudaFree(s->agg_tab); cudaFree(s->agg_met);
     cudaFree(s->d_part); cudaFree(s->d_scal); cudaFree(s->d_iters);
     cudaFreeHost(s->h_scal); cudaFreeHost(s->h_iters);
@@ -1910,6 +2057,7 @@ int sarasmg_op_vcycle(sarasmg_handle s, int *coarse_iters) {
     ENTER(s);
     *s->h_iters = 0;
     TRY(op_vcycle(s, nullptr));
+    TRY(finalize_pads(s));
     CU(cudaStreamSynchronize(s->st));
     s->last_coarse_iters = *s->h_iters;
     if (coarse_iters) *coarse_iters = s->last_coarse_iters;

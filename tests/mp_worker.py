@@ -121,13 +121,18 @@ def run_gpu(rank, world, local):
     # the V-cycle is replayed as a CUDA graph on every rank by default (peer-memory exchanges and the coarsest-level gathers
     # inside); one case with eager launches as well
     cases.append(dict(cases[0], name=cases[0]["name"] + "_nograph", _env="SARASMG_GRAPH_MULTI=0"))
+    # the Jacobi sweeps of mgSolve / vCycle push their boundary planes into the neighbours' pads (peer memory); the small
+    # grids above run the register-marching sweep: force the TMA-staged one too, and run one case with the push switched off
+    cases.append(dict(cases[0], name=cases[0]["name"] + "_push_tma", _env="SARASMG_TMA_MIN=3"))
+    cases.append(dict(cases[1], name=cases[1]["name"] + "_push_tma", _env="SARASMG_TMA_MIN=3"))
+    cases.append(dict(cases[2], name=cases[2]["name"] + "_nopush", _env="SARASMG_NO_PUSH=1"))
     if os.environ.get("MP_CASES"):      # comma-separated case names (debugging on a budget)
         cases = [c for c in cases if c["name"] in os.environ["MP_CASES"].split(",")]
     if world >= 8:      # an 8-GPU box is charged eight-fold: the six core cases plus one of each variant
-        cases = cases[:ncore] + [c for c in cases[ncore:] if c["name"].startswith("nnn")]
+        cases = cases[:ncore] + [c for c in cases[ncore:] if c["name"].startswith("nnn") or c["name"].endswith("_nopush")]
     for case in cases:
         base = {k: v for k, v in case.items() if k not in ("name", "_env")}
-        for key in ("SARASMG_COARSE_LEGACY", "SARASMG_HALO", "SARASMG_IPC_CTA_MAX", "SARASMG_GRAPH_MULTI"):
+        for key in ("SARASMG_COARSE_LEGACY", "SARASMG_HALO", "SARASMG_IPC_CTA_MAX", "SARASMG_GRAPH_MULTI", "SARASMG_TMA_MIN", "SARASMG_NO_PUSH"):
             os.environ.pop(key, None)
         if case.get("_env"):
             key, val = case["_env"].split("=")
