@@ -252,9 +252,8 @@ __device__ __forceinline__ void halo_push_signal(const HaloPush &H, const bool c
         if (cta_pushed) __threadfence_system();
         const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
         const unsigned t = atomicAdd(H.counter, 1u);
-        if (t == nb - 1) {
+        if (t == nb - 1) {               /* the flag stores are release.sys: cumulative over what the atomics made visible here */
             *H.counter = 0u;
-            __threadfence_system();
             const unsigned ep = *H.base + H.add;
 #pragma unroll
             for (int f = 0; f < 4; f++) ipc_signal(H.sflag[f], ep);
@@ -973,7 +972,7 @@ __device__ __forceinline__ void ipc_last_cta_signals(unsigned *counter, unsigned
     if (threadIdx.x == 0) {
         __threadfence_system();         /* one fence per CTA: cumulative over the stores the barrier ordered before it */
         const unsigned t = atomicAdd(counter, 1u);
-        if (t == gridDim.x - 1) { *counter = 0u; __threadfence_system(); ipc_signal(flag_a, epoch); ipc_signal(flag_b, epoch); }
+        if (t == gridDim.x - 1) { *counter = 0u; ipc_signal(flag_a, epoch); ipc_signal(flag_b, epoch); }    /* st.release.sys */
     }
 }
 __device__ __forceinline__ double ld_cg_f64(const double *p) { return __ldcg(p); }

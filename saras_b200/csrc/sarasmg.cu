@@ -18,6 +18,7 @@
 #include "gs_skew.cuh"
 #include "gs_strip.cuh"
 #include "mg_tma.cuh"
+#include "mg_fused.cuh"
 #include "proj_kernels.cuh"
 
 #include <nccl.h>
@@ -79,6 +80,7 @@ struct Level {
                                is its mapped slab + off; swapped together with buf[] */
     CUtensorMap tmapP[3];   /* TMA descriptors of the three arrays for the pressure box (with halo ring) ... */
     CUtensorMap tmapR[3];   /* ... and for the right-hand-side box; swapped together with buf[] */
+    CUtensorMap tmapP16[3], tmapR16[3];     /* the same for the 16-row tiles of the fused residual + restriction kernel (mg_fused.cuh) */
     bool tma;               /* level is large enough for k_stencil_tma and the descriptors exist */
     double *met[6];         /* device metric arrays (padded, base -1) */
     size_t elems;           /* allocated doubles per array */
@@ -167,6 +169,8 @@ struct sarasmg_solver_s {
     int prof_max_level;         /* events only for operators on levels <= this */
     bool coarsen_legacy;        /* SARASMG_COARSEN_LEGACY: thread-per-coarse-point restriction kernel */
     bool prolong_legacy;        /* SARASMG_PROLONG_LEGACY: thread-per-fine-point prolongation kernel */
+    double fuse_min_points;     /* fused residual + restriction on levels with at least this many core points */
+    bool no_fuse;               /* SARASMG_NO_FUSE: computeResidual and coarsen as two passes on every level */
     bool no_pow2;               /* SARASMG_NO_POW2: keep the general exact-division path even when the divisors are powers of two (tests) */
     bool gs_legacy;             /* SARASMG_GS_LEGACY: one launch per hyperplane instead of the skewed single-launch sweep */
     cudaEvent_t user_ev[8];
@@ -587,6 +591,12 @@ static int make_level_tmaps(S *s, Level &L) {
         CUresult r2 = enc(&L.tmapR[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, L.buf[a], dims, strides, boxR, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return set_err("cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+        const cuuint32_t boxP16[3] = {MG_FZ + 4, MG_FY + 2, 1}, boxR16[3] = {MG_FZ, MG_FY, 1};
+        r1 = enc(&L.tmapP16[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, L.buf[a], dims, strides, boxP16, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        r2 = enc(&L.tmapR16[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, L.buf[a], dims, strides, boxR16, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return set_err("cuTensorMapEncodeTiled (16-row tiles) failed (%d, %d)", (int)r1, (int)r2);
     }
     L.tma = true;
     return 0;
@@ -858,6 +868,8 @@ static int op_smooth(S *s, int count) {
                 std::swap(L.off[SARASMG_PRESSURE], L.off[SARASMG_TMP]);
                 std::swap(L.tmapP[SARASMG_PRESSURE], L.tmapP[SARASMG_TMP]);
                 std::swap(L.tmapR[SARASMG_PRESSURE], L.tmapR[SARASMG_TMP]);
+                std::swap(L.tmapP16[SARASMG_PRESSURE], L.tmapP16[SARASMG_TMP]);
+                std::swap(L.tmapR16[SARASMG_PRESSURE], L.tmapR16[SARASMG_TMP]);
             }
         }
         s->bucket = 0;
@@ -918,6 +930,50 @@ static int op_coarsen(S *s) {
         k_coarsen_march<<<dim3(gx, gy, cdiv(Lc.v.nx, ichunk)), dim3(bx, by, 1), 0, s->st>>>(Lf.buf[SARASMG_TMP], Lf.v, Lc.buf[SARASMG_RESIDUAL], Lc.v, ichunk);
     }
     return kcheck(s, "k_coarsen");
+}
+
+/* computeResidual + coarsen of the V-cycle (p:250-254) as one pass on the TMA levels (mg_fused.cuh): interior coarse points
+ * straight from pressure and rhs, the coarse faces through a two-plane shell of tmpDataArray with the usual pad handling.
+ * tmpDataArray's interior is NOT written: nothing reads it before the next sweep / residual overwrites it. */
+static bool fuse_level_ok(const S *s, int level) {
+    if (s->planar || s->no_fuse || level >= s->D) return false;
+    const Level &Lf = s->lev[level], &Lc = s->lev[level + 1];
+    if (!(Lf.tma && Lc.v.nx >= 3 && Lc.v.ny >= 3 && Lc.v.nz >= 3 && Lf.v.nx >= 5 && Lf.v.ny >= 5 && Lf.v.nz >= 5)) return false;
+    /* measured (mg_fused.cuh): the fused pass wins on the largest levels only; SARASMG_FUSE_MIN overrides the threshold (tests: 0) */
+    return (double)Lf.v.nx * Lf.v.ny * Lf.v.nz >= s->fuse_min_points;
+}
+static int op_residual_coarsen_fused(S *s) {
+    const int l = s->vLevel;
+    Level &Lf = s->lev[l];
+    Level &Lc = s->lev[l + 1];
+    double *P = Lf.buf[SARASMG_PRESSURE], *R = Lf.buf[SARASMG_RESIDUAL], *T = Lf.buf[SARASMG_TMP];
+    const LevelView &v = Lf.v, &c = Lc.v;
+    const bool p2 = divisors_pow2(false, v.hx * v.hx, v.hx, v.hy, v.hz * v.hz, v.hz) && !s->no_pow2;
+    TRY(zero_pads(s, l, T));
+    {
+        ProfScope ps(s, SARASMG_K_RESIDUAL, l);
+        const long long cnt = 4LL * v.ny * v.nz + 4LL * (v.nx - 4) * v.nz + 4LL * (v.nx - 4) * (v.ny - 4);
+        if (p2) k_resid_shell<true><<<face_blocks(cnt), 256, 0, s->st>>>(P, R, T, v);
+        else k_resid_shell<false><<<face_blocks(cnt), 256, 0, s->st>>>(P, R, T, v);
+        TRY(kcheck(s, "k_resid_shell"));
+        /* interior: independent of the shell and of every pad */
+        int CI = MG_F_MAXCI;
+        const unsigned gx = cdiv(c.nz - 2, MG_F_CK), gy = cdiv(c.ny - 2, MG_F_CJ);
+        while (CI > 4 && (long long)gx * gy * cdiv(c.nx - 2, CI) < 148LL * 4) CI = (CI + 1) / 2;
+        const dim3 grid(gx, gy, cdiv(c.nx - 2, CI)), block(MG_FZ / 2, MG_FY / 2, 1);
+        if (p2) k_resid_coarsen_tma<true><<<grid, block, MG_F_SMEM, s->st>>>(Lf.tmapP16[SARASMG_PRESSURE], Lf.tmapR16[SARASMG_RESIDUAL], v, Lc.buf[SARASMG_RESIDUAL], c, CI);
+        else k_resid_coarsen_tma<false><<<grid, block, MG_F_SMEM, s->st>>>(Lf.tmapP16[SARASMG_PRESSURE], Lf.tmapR16[SARASMG_RESIDUAL], v, Lc.buf[SARASMG_RESIDUAL], c, CI);
+        TRY(kcheck(s, "k_resid_coarsen_tma"));
+    }
+    TRY(update_pads(s, l, T));
+    s->vLevel += 1;
+    {
+        ProfScope ps(s, SARASMG_K_COARSEN, l);
+        const long long cnt = 2LL * c.ny * c.nz + 2LL * (c.nx - 2) * c.nz + 2LL * (c.nx - 2) * (c.ny - 2);
+        k_coarsen_shell<<<face_blocks(cnt), 256, 0, s->st>>>(T, v, Lc.buf[SARASMG_RESIDUAL], c);
+        TRY(kcheck(s, "k_coarsen_shell"));
+    }
+    return 0;
 }
 
 /* prolong (d3:301-365, d2:239-271) fused with pressureData += smoothedPres (p:271): vLevel -= 1 */
@@ -1326,9 +1382,12 @@ static int op_vcycle_body(S *s) {
     TRY(op_smooth(s, s->d.pre_smooth));
     s->zeroBC = 1;
     for (int i = 0; i < D; i++) {
-        TRY(op_compute_residual(s));
         /* p:252 smoothedPres = pressureData: kept in place (see header comment) */
-        TRY(op_coarsen(s));
+        if (fuse_level_ok(s, s->vLevel)) TRY(op_residual_coarsen_fused(s));
+        else {
+            TRY(op_compute_residual(s));
+            TRY(op_coarsen(s));
+        }
         {   /* p:258 pressureData(vLevel) = 0 */
             Level &L = s->lev[s->vLevel];
             ProfScope ps(s, SARASMG_K_MISC, s->vLevel);
@@ -1407,6 +1466,8 @@ static int run_vcycle(S *s) {
                 std::swap(L.off[SARASMG_PRESSURE], L.off[SARASMG_TMP]);
                 std::swap(L.tmapP[SARASMG_PRESSURE], L.tmapP[SARASMG_TMP]);
                 std::swap(L.tmapR[SARASMG_PRESSURE], L.tmapR[SARASMG_TMP]);
+                std::swap(L.tmapP16[SARASMG_PRESSURE], L.tmapP16[SARASMG_TMP]);
+                std::swap(L.tmapR16[SARASMG_PRESSURE], L.tmapR16[SARASMG_TMP]);
             }
         s->vLevel = 0;
         s->zeroBC = 0;
@@ -1567,6 +1628,8 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     s->no_pow2 = getenv("SARASMG_NO_POW2") != nullptr;
     s->prolong_legacy = getenv("SARASMG_PROLONG_LEGACY") != nullptr;
     s->coarsen_legacy = getenv("SARASMG_COARSEN_LEGACY") != nullptr;
+    s->no_fuse = getenv("SARASMG_NO_FUSE") != nullptr;
+    s->fuse_min_points = getenv("SARASMG_FUSE_MIN") ? atof(getenv("SARASMG_FUSE_MIN")) : (getenv("SARASMG_TMA_MIN") ? 0.0 : 4.0e8);   /* tests that force the TMA kernels onto small grids get the fused pass too */
     for (int q = 0; q < 8; q++) s->user_ev[q] = nullptr;
     s->proj_ok = false; s->d_presP = nullptr;
     for (int q = 0; q < 3; q++) { s->d_vel[q] = nullptr; s->vel_elems[q] = 0; }
@@ -1676,6 +1739,8 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     CU(cudaFuncSetAttribute(k_stencil_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
     CU(cudaFuncSetAttribute(k_stencil_tma_push<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
     CU(cudaFuncSetAttribute(k_stencil_tma_push<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
+    CU(cudaFuncSetAttribute(k_resid_coarsen_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_F_SMEM));
+    CU(cudaFuncSetAttribute(k_resid_coarsen_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_F_SMEM));
     CU(cudaFuncSetAttribute(k_stencil_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
     CU(cudaFuncSetAttribute(k_stencil_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));
     CU(cudaFuncSetAttribute(k_stencil_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_TMA_SMEM));

@@ -382,3 +382,34 @@ def test_gs_strip_default_geometry_257_against_oracle(monkeypatch):
     np.testing.assert_allclose(got["residuals"], ref["residuals"], rtol=1e-10, atol=0)
     assert np.array_equal(p, p_ref), max_abs(p - p_ref)
     s.close()
+
+
+@pytest.mark.parametrize("case", [dict(name="nnn_tanh", xGrid=2, zGrid=2, betaX=1.2, betaZ=1.4), dict(name="ppp", xPer=1, yPer=1, zPer=1),
+                                  dict(name="testpoisson", test_poisson=1)], ids=lambda c: c["name"])
+def test_fused_residual_restriction_equals_two_passes(case, monkeypatch):
+    """The V-cycle's computeResidual + coarsen runs as one pass on the large levels (mg_fused.cuh: interior coarse points straight
+    from pressure and rhs, coarse faces through a two-plane shell).  65 x 65 x 257 spans several tiles of the fused kernel in y,
+    z and x; the cycle must match the oracle bit for bit, and so must the two-pass cycle (SARASMG_NO_FUSE) -- whose launch count
+    differs, which shows that the fused pass really ran."""
+    monkeypatch.setenv("SARASMG_TMA_MIN", "17")
+    extra = {k: v for k, v in case.items() if k != "name"}
+    outs, launches = [], []
+    for no_fuse in (False, True):
+        if no_fuse:
+            monkeypatch.setenv("SARASMG_NO_FUSE", "1")
+        o, s = _mk(dict(name="fused", dim=3, xInd=6, yInd=6, zInd=8, vcDepth=3, gsSmooth=0, **extra))
+        _, F = o.level_dims(0)
+        _load_both(o, s, 0, mo.PRESSURE, seeded_field(F, 300, 0.1))
+        _load_both(o, s, 0, mo.RESIDUAL, seeded_field(F, 301, 2.0))
+        n0 = s.kernel_launches()
+        for _ in range(2):
+            o.vcycle(); s.vcycle()
+        launches.append(s.kernel_launches() - n0)
+        got = s.level_get(0, capi.PRESSURE)
+        assert np.array_equal(got, o.array(0, 0, mo.PRESSURE)), max_abs(got - o.array(0, 0, mo.PRESSURE))
+        for level in range(1, o.depth + 1):
+            assert np.array_equal(s.level_get(level, capi.RESIDUAL), o.array(0, level, mo.RESIDUAL)), level
+        outs.append(got)
+        s.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert launches[0] != launches[1], launches
