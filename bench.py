@@ -46,7 +46,8 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 METRIC = "multigrid_vcycle_glups"
 UNIT = "GLUP/s"
 LAYOUTS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}
-BYTES_PER_LUP = {"smooth": 24.0, "residual": 24.0, "coarsen": 9.0, "prolong": 17.0, "error": 16.0}
+BYTES_PER_LUP = {"smooth": 24.0, "residual": 24.0, "coarsen": 9.0, "prolong": 17.0, "error": 16.0,
+                 "residual+coarsen": 17.0}     # the fused pass of the largest levels: read p, read rhs, write 1/8 coarse rhs
 GS_KERNEL = "k_gs_skew<3> lexicographic Gauss-Seidel"
 
 
@@ -391,10 +392,12 @@ def run_b200(a):
         rows = []
         for lvl in range(min(2, depth + 1)):
             for kind, name in ((capi.K_SMOOTH, "smooth"), (capi.K_RESIDUAL, "residual"), (capi.K_COARSEN, "coarsen"),
-                               (capi.K_PROLONG, "prolong"), (capi.K_ERROR, "error")):
+                               (capi.K_FUSED_RC, "residual+coarsen"), (capi.K_PROLONG, "prolong"), (capi.K_ERROR, "error")):
                 ms, n = s.profile_query(kind, lvl)
                 if n == 0:
                     continue
+                if name == "residual+coarsen":
+                    n //= 2                 # two event pairs per fused pass (shell residual + fused kernel, shell restriction)
                 pts = level_points_local[lvl]
                 gbs = BYTES_PER_LUP[name] * pts / (ms / n * 1e-3) / 1e9
                 rows.append(dict(level=lvl, op=name, launches=int(n), avg_ms=ms / n, gbs=gbs, frac=gbs / peak))
@@ -444,11 +447,13 @@ def run_b200(a):
     per_level_all = []
     for lvl in range(depth + 1):
         for kind, name in ((capi.K_SMOOTH, "smooth"), (capi.K_RESIDUAL, "residual"), (capi.K_COARSEN, "coarsen"),
-                           (capi.K_PROLONG, "prolong"), (capi.K_ERROR, "error"), (capi.K_HALO, "halo"), (capi.K_BC, "bc"),
-                           (capi.K_COARSE_SOLVE, "coarse_solve")):
+                           (capi.K_FUSED_RC, "residual+coarsen"), (capi.K_PROLONG, "prolong"), (capi.K_ERROR, "error"), (capi.K_HALO, "halo"),
+                           (capi.K_BC, "bc"), (capi.K_COARSE_SOLVE, "coarse_solve")):
             ms, n = s.profile_query(kind, lvl)
             if n == 0:
                 continue
+            if name == "residual+coarsen":
+                n //= 2
             e = dict(level=lvl, op=name, launches=int(n), avg_us=1e3 * ms / n)
             if name in BYTES_PER_LUP:
                 gbs = BYTES_PER_LUP[name] * level_points_local[lvl] / (ms / n * 1e-3) / 1e9

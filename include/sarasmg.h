@@ -115,7 +115,9 @@ int sarasmg_download(sarasmg_handle h, double *p_out);
  * divergence -> mgSolve -> correction without touching the host; Pp stays resident as the next step's initial guess.
  * Field layouts are the reference's Blitz arrays (base -1, z fastest; lib/field/field.cc:66-105): Vx (nx+1, ny+2, nz+2),
  * Vy (nx+2, ny+1, nz+2), Vz (nx+2, ny+2, nz+1), P / Pp / mgRHS (nx+2, ny+2, nz+2), nx.. = n0[] of the descriptor.
- * One rank only for now (Pp.syncData between ranks is row 8f-2), multigrid_d3 only. */
+ * Several ranks: Pp.syncData() exchanges the four faces with face_ranks (core rows only) and the four edge
+ * columns with the diagonal ranks (always the periodic wrap, parallel.cc:124-129) in one grouped ncclSend/ncclRecv on the
+ * solver's communicator.  multigrid_d3 only. */
 typedef struct {
     const double *xi_x_staggr, *et_y_staggr, *zt_z_staggr;   /* grid::xi_xStaggr ..: n_d + 2 doubles, first entry is index -1 */
     const double *xi_x_colloc, *et_y_colloc, *zt_z_colloc;   /* grid::xi_xColloc ..: n_d + 1 doubles, first entry is index -1 */
@@ -163,7 +165,8 @@ long long sarasmg_kernel_launches(sarasmg_handle h);
 int sarasmg_reset_counters(sarasmg_handle h);
 /* operator classes for profiling */
 enum { SARASMG_K_SMOOTH = 0, SARASMG_K_RESIDUAL, SARASMG_K_COARSEN, SARASMG_K_PROLONG, SARASMG_K_ERROR,
-       SARASMG_K_BC, SARASMG_K_COARSE_SOLVE, SARASMG_K_HALO, SARASMG_K_MISC, SARASMG_K_COUNT };
+       SARASMG_K_BC, SARASMG_K_COARSE_SOLVE, SARASMG_K_HALO, SARASMG_K_MISC,
+       SARASMG_K_FUSED_RC /* computeResidual + coarsen as one pass (largest levels) */, SARASMG_K_COUNT };
 /* with SARASMG_FLAG_PROFILE: accumulated CUDA-event time (ms) and launch count of operator class `kind` on `level`
  * since the last sarasmg_reset_counters.  Synchronises the stream. */
 int sarasmg_profile_query(sarasmg_handle h, int kind, int level, double *total_ms, long long *launches);

@@ -90,6 +90,8 @@ def _load(fast=False):
     lib.projo_divergence.argtypes = [C.c_int] * 3 + [dp] * 6 + [C.c_double] * 4 + [dp]
     lib.projo_sync_one_rank.argtypes = [C.c_int] * 5 + [dp]
     lib.projo_correct.argtypes = [C.c_int] * 5 + [dp] * 8 + [C.c_double] * 4
+    lib.projo_sync_multi.argtypes = [C.c_int] * 7 + [C.POINTER(dp)]
+    lib.projo_correct_nosync.argtypes = [C.c_int] * 3 + [dp] * 8 + [C.c_double] * 4
     lib.mgo_lup_count.argtypes = [vp]
     _LIBS[key] = lib
     return lib
@@ -297,3 +299,18 @@ def proj_correct(n, xper, yper, pp, P, vx, vy, vz, coll, spacing, dt):
     """in place on pp (syncData), P, vx, vy, vz"""
     _load().projo_correct(n[0], n[1], n[2], int(xper), int(yper), _dpp(pp), _dpp(P), _dpp(vx), _dpp(vy), _dpp(vz),
                           _dpp(coll[0]), _dpp(coll[1]), _dpp(coll[2]), spacing[0], spacing[1], spacing[2], dt)
+
+
+def proj_sync_multi(o, pp_list):
+    """Pp.syncData() on all ranks of Oracle `o` at once (in place on every array of pp_list, rank order)"""
+    n, _ = o.level_dims(0)
+    c = o.cfg
+    dp = C.POINTER(C.c_double)
+    ptrs = (dp * o.nranks)(*[_dpp(a) for a in pp_list])
+    _load().projo_sync_multi(c["npX"], c["npY"], n[0], n[1], n[2], int(c["xPer"]), int(c["yPer"]), ptrs)
+
+
+def proj_correct_nosync(n, pp, P, vx, vy, vz, coll, spacing, dt):
+    """P += Pp; V -= dt grad(Pp) of one rank whose Pp is already synchronised; in place on P, vx, vy, vz"""
+    _load().projo_correct_nosync(n[0], n[1], n[2], _dpp(pp), _dpp(P), _dpp(vx), _dpp(vy), _dpp(vz),
+                                 _dpp(coll[0]), _dpp(coll[1]), _dpp(coll[2]), spacing[0], spacing[1], spacing[2], dt)

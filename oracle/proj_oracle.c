@@ -115,3 +115,58 @@ void projo_correct(int nx, int ny, int nz, int xper, int yper, double *pp, doubl
         vz[VZ(i, j, k)] -= g;
     }
 }
+
+/* mpidata::syncData of a staggered scalar on npX x npY ranks (mpidata.cc:278-306), all ranks emulated in one process:
+ * A[r] is rank r's array (rank = yRank * npX + xRank, parallel.cc:89-92).  Faces go to faceRanks -- the periodic wrap,
+ * nulled at the walls of a non-periodic direction by hydro::checkPeriodic (hydro.cc:174-203) -- and carry core rows only;
+ * edges go to edgeRanks, the periodic wrap whatever the domain type (parallel.cc:124-129).  Every message is read from core
+ * points and written to pads, so the order of the eight messages does not matter. */
+static int projo_find_rank(int xr, int yr, int npX, int npY) { return ((yr + npY) % npY) * npX + ((xr + npX) % npX); }
+void projo_sync_multi(int npX, int npY, int nx, int ny, int nz, int xper, int yper, double *const *A) {
+    for (int r = 0; r < npX * npY; r++) {
+        const int xr = r % npX, yr = r / npX;
+        double *D = A[r];
+        if (xper || xr > 0) {               /* left pad <- left neighbour's plane nx-2 */
+            const double *S = A[projo_find_rank(xr - 1, yr, npX, npY)];
+            for (int j = 0; j < ny; j++) for (int k = 0; k < nz; k++) D[SC(-1, j, k)] = S[SC(nx - 2, j, k)];
+        }
+        if (xper || xr < npX - 1) {
+            const double *S = A[projo_find_rank(xr + 1, yr, npX, npY)];
+            for (int j = 0; j < ny; j++) for (int k = 0; k < nz; k++) D[SC(nx, j, k)] = S[SC(1, j, k)];
+        }
+        if (yper || yr > 0) {
+            const double *S = A[projo_find_rank(xr, yr - 1, npX, npY)];
+            for (int i = 0; i < nx; i++) for (int k = 0; k < nz; k++) D[SC(i, -1, k)] = S[SC(i, ny - 2, k)];
+        }
+        if (yper || yr < npY - 1) {
+            const double *S = A[projo_find_rank(xr, yr + 1, npX, npY)];
+            for (int i = 0; i < nx; i++) for (int k = 0; k < nz; k++) D[SC(i, ny, k)] = S[SC(i, 1, k)];
+        }
+        for (int xh = 0; xh < 2; xh++) for (int yh = 0; yh < 2; yh++) {
+            const double *S = A[projo_find_rank(xr + (xh ? 1 : -1), yr + (yh ? 1 : -1), npX, npY)];
+            for (int k = 0; k < nz; k++) D[SC(xh ? nx : -1, yh ? ny : -1, k)] = S[SC(xh ? 1 : nx - 2, yh ? 1 : ny - 2, k)];
+        }
+    }
+}
+
+/* the correction step of one rank AFTER its Pp has been synchronised (projo_sync_multi): P += Pp; V -= dt grad(Pp) */
+void projo_correct_nosync(int nx, int ny, int nz, const double *pp, double *P, double *vx, double *vy, double *vz,
+                          const double *xc, const double *yc, const double *zc, double dXi, double dEt, double dZt, double dt) {
+    const size_t n = (size_t)(nx + 2) * (ny + 2) * (nz + 2);
+    for (size_t q = 0; q < n; q++) P[q] += pp[q];
+    for (int i = 0; i <= nx - 2; i++) for (int j = 0; j < ny; j++) for (int k = 0; k < nz; k++) {
+        double g = xc[i + 1] * (pp[SC(i + 1, j, k)] - pp[SC(i, j, k)]) / dXi;
+        g *= dt;
+        vx[VX(i, j, k)] -= g;
+    }
+    for (int i = 0; i < nx; i++) for (int j = 0; j <= ny - 2; j++) for (int k = 0; k < nz; k++) {
+        double g = yc[j + 1] * (pp[SC(i, j + 1, k)] - pp[SC(i, j, k)]) / dEt;
+        g *= dt;
+        vy[VY(i, j, k)] -= g;
+    }
+    for (int i = 0; i < nx; i++) for (int j = 0; j < ny; j++) for (int k = 0; k <= nz - 2; k++) {
+        double g = zc[k + 1] * (pp[SC(i, j, k + 1)] - pp[SC(i, j, k)]) / dZt;
+        g *= dt;
+        vz[VZ(i, j, k)] -= g;
+    }
+}

@@ -17,8 +17,8 @@ UNIQUE_ID_BYTES = 128
 FLAG_TIME_RUN = 1
 FLAG_PROFILE = 2
 PRESSURE, RESIDUAL, TMP = 0, 1, 2
-K_SMOOTH, K_RESIDUAL, K_COARSEN, K_PROLONG, K_ERROR, K_BC, K_COARSE_SOLVE, K_HALO, K_MISC = range(9)
-KIND_NAMES = ["smooth", "residual", "coarsen", "prolong", "error", "bc", "coarse_solve", "halo", "misc"]
+K_SMOOTH, K_RESIDUAL, K_COARSEN, K_PROLONG, K_ERROR, K_BC, K_COARSE_SOLVE, K_HALO, K_MISC, K_FUSED_RC = range(10)
+KIND_NAMES = ["smooth", "residual", "coarsen", "prolong", "error", "bc", "coarse_solve", "halo", "misc", "residual+coarsen"]
 
 _dp = C.POINTER(C.c_double)
 

@@ -118,3 +118,61 @@ __global__ void __launch_bounds__(256) k_copy_padded(const double *__restrict__ 
         for (int k = threadIdx.x; k < L.Fz; k += blockDim.x) D[base + k] = S[base + k];
     }
 }
+
+/* ---- Pp.syncData() between ranks (mpidata.cc:278-306) ----
+ * One message per remote face (core rows only: ny x nz / nx x nz values, mpidata.cc:105-178) and one per edge (nz values of
+ * the core corner column, mpidata.cc:183-259).  Sources are core points only and destinations are disjoint pads, so faces and
+ * edges travel in ONE grouped ncclSend/ncclRecv.  Buffer layout (doubles): x faces [2][ny*nz], y faces [2][nx*nz], edges [4][nz];
+ * side order: x lo, x hi, y lo, y hi; edges (x lo,y lo), (x lo,y hi), (x hi,y lo), (x hi,y hi). */
+struct ProjSyncPlan {
+    int face_remote[4];         /* exchange this face with another rank (self-periodic and wall faces are not in the messages) */
+    long long off_face[4];      /* offsets of the face / edge blocks in the send and the receive buffer */
+    long long off_edge[4];
+};
+__global__ void __launch_bounds__(256) k_proj_sync_pack(const double *__restrict__ A, const LevelView L, const ProjSyncPlan P, double *__restrict__ buf) {
+    const long long nxf = (long long)L.ny * L.nz, nyf = (long long)L.nx * L.nz;
+    const long long tot = 2 * nxf + 2 * nyf + 4LL * L.nz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+        long long w = q;
+        if (w < 2 * nxf) {
+            const int hi = w >= nxf; w -= hi ? nxf : 0;
+            if (!P.face_remote[hi]) continue;
+            /* staggered fields share the boundary point: plane 1 goes left, plane nx-2 goes right (mpidata.cc:112, 131) */
+            buf[P.off_face[hi] + w] = A[mg_at(L, hi ? L.nx - 2 : 1, (int)(w / L.nz), (int)(w % L.nz))];
+            continue;
+        }
+        w -= 2 * nxf;
+        if (w < 2 * nyf) {
+            const int hi = w >= nyf; w -= hi ? nyf : 0;
+            if (!P.face_remote[2 + hi]) continue;
+            buf[P.off_face[2 + hi] + w] = A[mg_at(L, (int)(w / L.nz), hi ? L.ny - 2 : 1, (int)(w % L.nz))];
+            continue;
+        }
+        w -= 2 * nyf;
+        const int e = (int)(w / L.nz), k = (int)(w % L.nz);
+        buf[P.off_edge[e] + k] = A[mg_at(L, (e >> 1) ? L.nx - 2 : 1, (e & 1) ? L.ny - 2 : 1, k)];
+    }
+}
+__global__ void __launch_bounds__(256) k_proj_sync_unpack(double *__restrict__ A, const LevelView L, const ProjSyncPlan P, const double *__restrict__ buf) {
+    const long long nxf = (long long)L.ny * L.nz, nyf = (long long)L.nx * L.nz;
+    const long long tot = 2 * nxf + 2 * nyf + 4LL * L.nz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+        long long w = q;
+        if (w < 2 * nxf) {
+            const int hi = w >= nxf; w -= hi ? nxf : 0;
+            if (!P.face_remote[hi]) continue;
+            A[mg_at(L, hi ? L.nx : -1, (int)(w / L.nz), (int)(w % L.nz))] = buf[P.off_face[hi] + w];
+            continue;
+        }
+        w -= 2 * nxf;
+        if (w < 2 * nyf) {
+            const int hi = w >= nyf; w -= hi ? nyf : 0;
+            if (!P.face_remote[2 + hi]) continue;
+            A[mg_at(L, (int)(w / L.nz), hi ? L.ny : -1, (int)(w % L.nz))] = buf[P.off_face[2 + hi] + w];
+            continue;
+        }
+        w -= 2 * nyf;
+        const int e = (int)(w / L.nz), k = (int)(w % L.nz);
+        A[mg_at(L, (e >> 1) ? L.nx : -1, (e & 1) ? L.ny : -1, k)] = buf[P.off_edge[e] + k];
+    }
+}

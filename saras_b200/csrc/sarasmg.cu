@@ -182,6 +182,9 @@ struct sarasmg_solver_s {
     size_t vel_elems[3];
     double *d_presP;            /* P in the pitched level-0 layout */
     double *d_pmet[6];          /* xi_xStaggr, et_yStaggr, zt_zStaggr, xi_xColloc, et_yColloc, zt_zColloc */
+    double *d_psync[2];         /* send / receive buffer of Pp.syncData() between ranks */
+    ProjSyncPlan psync;
+    int edge_ranks[4];          /* parallel.cc:124-129: always the periodic wrap, never nulled by checkPeriodic */
 };
 
 typedef sarasmg_solver_s S;
@@ -951,7 +954,7 @@ static int op_residual_coarsen_fused(S *s) {
     const bool p2 = divisors_pow2(false, v.hx * v.hx, v.hx, v.hy, v.hz * v.hz, v.hz) && !s->no_pow2;
     TRY(zero_pads(s, l, T));
     {
-        ProfScope ps(s, SARASMG_K_RESIDUAL, l);
+        ProfScope ps(s, SARASMG_K_FUSED_RC, l);
         const long long cnt = 4LL * v.ny * v.nz + 4LL * (v.nx - 4) * v.nz + 4LL * (v.nx - 4) * (v.ny - 4);
         if (p2) k_resid_shell<true><<<face_blocks(cnt), 256, 0, s->st>>>(P, R, T, v);
         else k_resid_shell<false><<<face_blocks(cnt), 256, 0, s->st>>>(P, R, T, v);
@@ -968,7 +971,7 @@ static int op_residual_coarsen_fused(S *s) {
     TRY(update_pads(s, l, T));
     s->vLevel += 1;
     {
-        ProfScope ps(s, SARASMG_K_COARSEN, l);
+        ProfScope ps(s, SARASMG_K_FUSED_RC, l);
         const long long cnt = 2LL * c.ny * c.nz + 2LL * (c.nx - 2) * c.nz + 2LL * (c.nx - 2) * (c.ny - 2);
         k_coarsen_shell<<<face_blocks(cnt), 256, 0, s->st>>>(T, v, Lc.buf[SARASMG_RESIDUAL], c);
         TRY(kcheck(s, "k_coarsen_shell"));
@@ -1634,6 +1637,7 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     s->proj_ok = false; s->d_presP = nullptr;
     for (int q = 0; q < 3; q++) { s->d_vel[q] = nullptr; s->vel_elems[q] = 0; }
     for (int q = 0; q < 6; q++) s->d_pmet[q] = nullptr;
+    s->d_psync[0] = s->d_psync[1] = nullptr;
     memset(s->prof_ms, 0, sizeof(s->prof_ms));
     memset(s->prof_n, 0, sizeof(s->prof_n));
     for (int q = 0; q < 3; q++) s->d_wall[q] = nullptr;
@@ -1860,6 +1864,7 @@ int sarasmg_destroy(sarasmg_handle s) {
     cudaFree(s->d_in_p); cudaFree(s->d_in_rhs);
     for (int q = 0; q < 3; q++) cudaFree(s->d_vel[q]);
     for (int q = 0; q < 6; q++) cudaFree(s->d_pmet[q]);
+    cudaFree(s->d_psync[0]); cudaFree(s->d_psync[1]);
     cudaFree(s->d_presP);
     for (auto &e : s->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto &e : s->ev_pool) cudaEventDestroy(e);
@@ -1954,7 +1959,6 @@ int sarasmg_solve(sarasmg_handle s, double *p_inout, const double *rhs, int *cyc
 int sarasmg_proj_setup(sarasmg_handle s, const sarasmg_proj_desc *d) {
     if (!s || !d) return set_err("sarasmg_proj_setup: null argument");
     if (s->planar) return set_err("sarasmg_proj_setup: the device-resident projection step is built for multigrid_d3 only");
-    if (s->d.n_proc != 1) return set_err("sarasmg_proj_setup: one rank only (Pp.syncData across ranks, mpidata.cc:278-306, is SURVEY row 8f-2)");
     if (!d->xi_x_staggr || !d->et_y_staggr || !d->zt_z_staggr || !d->xi_x_colloc || !d->et_y_colloc || !d->zt_z_colloc)
         return set_err("sarasmg_proj_setup: null metric array");
     CU(cudaSetDevice(s->d.device));
@@ -1979,6 +1983,23 @@ int sarasmg_proj_setup(sarasmg_handle s, const sarasmg_proj_desc *d) {
         s->vel_elems[q] = ve[q];
         if (!s->d_vel[q]) CU(cudaMalloc(&s->d_vel[q], sizeof(double) * ve[q]));
         CU(cudaMemsetAsync(s->d_vel[q], 0, sizeof(double) * ve[q], s->st));
+    }
+    {   /* Pp.syncData() between ranks: face / edge partners and the message buffers */
+        const sarasmg_desc &dd = s->d;
+        const int me = dd.rank;
+        auto find_rank = [&](int xr, int yr) { return ((yr + dd.npy) % dd.npy) * dd.npx + ((xr + dd.npx) % dd.npx); };   /* parallel.cc:133-160 */
+        s->edge_ranks[0] = find_rank(dd.x_rank - 1, dd.y_rank - 1); s->edge_ranks[1] = find_rank(dd.x_rank - 1, dd.y_rank + 1);
+        s->edge_ranks[2] = find_rank(dd.x_rank + 1, dd.y_rank - 1); s->edge_ranks[3] = find_rank(dd.x_rank + 1, dd.y_rank + 1);
+        const long long nxf = (long long)v0.ny * v0.nz, nyf = (long long)v0.nx * v0.nz;
+        for (int f = 0; f < 4; f++) {
+            s->psync.face_remote[f] = (dd.face_ranks[f] != SARASMG_PROC_NULL && dd.face_ranks[f] != me) ? 1 : 0;
+            s->psync.off_face[f] = (f < 2) ? f * nxf : 2 * nxf + (f - 2) * nyf;
+            s->psync.off_edge[f] = 2 * nxf + 2 * nyf + (long long)f * v0.nz;
+        }
+        if (dd.n_proc > 1) {
+            const size_t tot = (size_t)(2 * nxf + 2 * nyf + 4LL * v0.nz);
+            for (int q = 0; q < 2; q++) if (!s->d_psync[q]) CU(cudaMalloc(&s->d_psync[q], tot * sizeof(double)));
+        }
     }
     if (!s->d_presP) CU(cudaMalloc(&s->d_presP, s->lev[0].elems * sizeof(double)));
     CU(cudaMemsetAsync(s->d_presP, 0, s->lev[0].elems * sizeof(double), s->st));
@@ -2020,13 +2041,43 @@ static int proj_correct(S *s, double dt) {
     /* inFn.F = pressureData(0) over the whole padded box (p:151): Pp, which is also the initial guess of the next solve */
     k_copy_padded<<<std::min(cdiv((long long)v0.Fx * v0.Fy, 1), 148u * 8u), 256, 0, s->st>>>(L0.buf[SARASMG_PRESSURE], s->d_in_p, v0);
     TRY(kcheck(s, "k_copy_padded"));
+    /* Pp.syncData() (hydro_d3.cc:347): faces with faceRanks, edges with edgeRanks */
     const int xper = (s->d.face_ranks[0] == s->d.rank) ? 1 : 0, yper = (s->d.face_ranks[2] == s->d.rank) ? 1 : 0;
-    if (xper || yper) {
+    if (xper || yper) {         /* this rank is its own neighbour along a periodic, unsplit axis */
         k_proj_sync_faces<<<std::min(cdiv(2LL * v0.ny * v0.nz + 2LL * v0.nx * v0.nz, 256), 2048u), 256, 0, s->st>>>(s->d_in_p, v0, xper, yper);
         TRY(kcheck(s, "k_proj_sync_faces"));
     }
-    k_proj_sync_edges<<<cdiv(4LL * v0.nz, 256), 256, 0, s->st>>>(s->d_in_p, v0);
-    TRY(kcheck(s, "k_proj_sync_edges"));
+    if (s->d.n_proc == 1) {
+        k_proj_sync_edges<<<cdiv(4LL * v0.nz, 256), 256, 0, s->st>>>(s->d_in_p, v0);
+        TRY(kcheck(s, "k_proj_sync_edges"));
+    } else {
+        if (!s->has_comm) return set_err("sarasmg_proj_correct: several ranks but no communicator");
+        const long long nxf = (long long)v0.ny * v0.nz, nyf = (long long)v0.nx * v0.nz;
+        const unsigned nb = std::min(cdiv(2 * nxf + 2 * nyf + 4LL * v0.nz, 256), 2048u);
+        k_proj_sync_pack<<<nb, 256, 0, s->st>>>(s->d_in_p, v0, s->psync, s->d_psync[0]);
+        TRY(kcheck(s, "k_proj_sync_pack"));
+        const int *fr = s->d.face_ranks, *er = s->edge_ranks;
+        const ProjSyncPlan &Q = s->psync;
+        double *sb = s->d_psync[0], *rb = s->d_psync[1];
+        const size_t fc[4] = {(size_t)nxf, (size_t)nxf, (size_t)nyf, (size_t)nyf};
+        NC(ncclGroupStart());
+        /* pairs (send one side, receive the opposite pad) keep messages matched when one peer is the neighbour on both sides */
+        for (int a = 0; a < 4; a += 2) {
+            if (Q.face_remote[a])     NC(ncclSend(sb + Q.off_face[a],     fc[a], ncclDouble, fr[a],     s->comm, s->st));
+            if (Q.face_remote[a + 1]) NC(ncclRecv(rb + Q.off_face[a + 1], fc[a], ncclDouble, fr[a + 1], s->comm, s->st));
+            if (Q.face_remote[a + 1]) NC(ncclSend(sb + Q.off_face[a + 1], fc[a], ncclDouble, fr[a + 1], s->comm, s->st));
+            if (Q.face_remote[a])     NC(ncclRecv(rb + Q.off_face[a],     fc[a], ncclDouble, fr[a],     s->comm, s->st));
+        }
+        /* edges: my (x lo, y lo) corner column lands in the (x hi, y hi) pad of edgeRanks(0), ... (mpidata.cc:296-305) */
+        const int pair[4][2] = {{0, 3}, {3, 0}, {1, 2}, {2, 1}};
+        for (int q = 0; q < 4; q++) {
+            NC(ncclSend(sb + Q.off_edge[pair[q][0]], (size_t)v0.nz, ncclDouble, er[pair[q][0]], s->comm, s->st));
+            NC(ncclRecv(rb + Q.off_edge[pair[q][1]], (size_t)v0.nz, ncclDouble, er[pair[q][1]], s->comm, s->st));
+        }
+        NC(ncclGroupEnd());
+        k_proj_sync_unpack<<<nb, 256, 0, s->st>>>(s->d_in_p, v0, s->psync, s->d_psync[1]);
+        TRY(kcheck(s, "k_proj_sync_unpack"));
+    }
     const dim3 grid(cdiv(v0.Fz, 128), v0.Fy, v0.Fx);
     k_proj_correct<<<grid, 128, 0, s->st>>>(s->d_in_p, s->d_presP, s->d_vel[0], s->d_vel[1], s->d_vel[2], v0, s->pv, dt);
     return kcheck(s, "k_proj_correct");

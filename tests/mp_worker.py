@@ -210,6 +210,34 @@ def run_gpu(rank, world, local):
                     check_natural_mean_field(o, p0, rhs, rank, p, p_ref, what)
                 else:
                     assert np.array_equal(p, p_ref[rank]), (what, mode, float(np.max(np.abs(p - p_ref[rank]))))
+            # device-resident projection step across ranks: divergence -> mgSolve -> Pp.syncData (faces with
+            # faceRanks, edges with edgeRanks over grouped ncclSend/ncclRecv) -> P += Pp -> V -= dt grad(Pp), two time steps
+            if cfg["dim"] == 3 and not cfg.get("test_poisson"):
+                n, _ = o.level_dims(0)
+                sh = mo.proj_shapes(n)
+                met = [mo.proj_metrics(o, r) for r in range(world)]
+                rng = np.random.default_rng(4242)
+                fld = [[np.ascontiguousarray(rng.uniform(-1.0, 1.0, sh[k])) for k in ("vx", "vy", "vz", "sc")] + [np.zeros(sh["sc"])] for _ in range(world)]
+                s.debug_set_rhs_mean(False)
+                o.set_exact_mean(True)
+                s.proj_setup(*met[rank])
+                for which, a in zip((capi.PROJ_VX, capi.PROJ_VY, capi.PROJ_VZ, capi.PROJ_P, capi.PROJ_PP), fld[rank]):
+                    s.proj_upload(which, a)
+                dt = 0.01
+                for step in range(2):
+                    got = s.proj_step(dt)
+                    rhs_l = [mo.proj_divergence(n, f[0], f[1], f[2], met[r][0], met[r][2], 1.0 / dt) for r, f in enumerate(fld)]
+                    pp_l = [f[4] for f in fld]
+                    refp = o.mg_solve(pp_l, rhs_l)
+                    mo.proj_sync_multi(o, pp_l)
+                    for r, f in enumerate(fld):
+                        mo.proj_correct_nosync(n, f[4], f[3], f[0], f[1], f[2], met[r][1], met[r][2], dt)
+                    assert got["cycles"] == refp["cycles"], (what, step, got["cycles"], refp["cycles"])
+                    np.testing.assert_allclose(got["residuals"], refp["residuals"], rtol=1e-10, atol=0)
+                    for which, ref_a, nm in zip((capi.PROJ_VX, capi.PROJ_VY, capi.PROJ_VZ, capi.PROJ_P, capi.PROJ_PP), fld[rank], ("Vx", "Vy", "Vz", "P", "Pp")):
+                        g = s.proj_download(which)
+                        assert np.array_equal(g, ref_a), "%s projection step %d: %s differs on rank %d, max |d| = %g" % (what, step, nm, rank, float(np.max(np.abs(g - ref_a))))
+                o.set_exact_mean(False)
             assert s.kernel_launches() > 0
             s.close()
             dist.barrier()

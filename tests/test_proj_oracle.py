@@ -83,3 +83,49 @@ def test_projection_oracle_against_numpy(g):
     mo.proj_correct(n, o.cfg["xPer"], o.cfg["yPer"], pp, P, vx, vy, vz, coll, sp, dt)
     for got, ref, what in zip((pp, P, vx, vy, vz), want, ("Pp", "P", "Vx", "Vy", "Vz")):
         assert np.array_equal(got, ref), what
+
+
+@pytest.mark.parametrize("lay", [(2, 1, 0, 0), (2, 2, 1, 1), (4, 2, 1, 0), (1, 2, 0, 1)], ids=lambda t: "np%dx%d_per%d%d" % t)
+def test_multirank_sync_is_the_global_periodic_wrap(lay):
+    """mpidata::syncData across ranks (projo_sync_multi) against a direct statement on the GLOBAL staggered field: every rank's
+    core is a window of one global array whose neighbouring windows share their boundary plane; after the exchange a pad holds
+    the global value one point outside the window -- across rank boundaries, and across the domain boundary where the
+    reference wraps (periodic faces; edges always, parallel.cc:124-129) -- and is untouched at wall faces."""
+    npx, npy, xper, yper = lay
+    o = Oracle(dim=3, xInd=5, yInd=5, zInd=3, vcDepth=1, npX=npx, npY=npy, xPer=xper, yPer=yper)
+    n, F = o.level_dims(0)
+    gx, gy = npx * (n[0] - 1), npy * (n[1] - 1)           # global intervals: global staggered points 0 .. gx, point gx == point 0 when periodic
+    rng = np.random.default_rng(5)
+    G = rng.uniform(-1, 1, (gx + 1, gy + 1, n[2]))
+    if xper:
+        G[gx] = G[0]
+    if yper:
+        G[:, gy] = G[:, 0]
+    arrs, before = [], []
+    for r in range(o.nranks):
+        xr, yr = r % npx, r // npx
+        a = rng.uniform(-1, 1, F)
+        a[1:-1, 1:-1, 1:-1] = G[xr * (n[0] - 1):xr * (n[0] - 1) + n[0], yr * (n[1] - 1):yr * (n[1] - 1) + n[1], :]
+        arrs.append(np.ascontiguousarray(a)); before.append(a.copy())
+    mo.proj_sync_multi(o, arrs)
+
+    def wrap(i, g):     # global staggered index of a point one step outside, on a ring of g intervals
+        return i % g
+
+    for r in range(o.nranks):
+        xr, yr = r % npx, r // npx
+        x0, y0 = xr * (n[0] - 1), yr * (n[1] - 1)
+        a = arrs[r]
+        assert np.array_equal(a[1:-1, 1:-1, :], before[r][1:-1, 1:-1, :])                   # cores and z pads untouched
+        for side, (li, gi) in enumerate(((0, x0 - 1), (n[0] + 1, x0 + n[0]))):
+            wall = not xper and ((side == 0 and xr == 0) or (side == 1 and xr == npx - 1))
+            want = before[r][li, 1:-1, 1:-1] if wall else G[wrap(gi, gx), y0:y0 + n[1], :]
+            assert np.array_equal(a[li, 1:-1, 1:-1], want), (r, "x", side)
+        for side, (lj, gj) in enumerate(((0, y0 - 1), (n[1] + 1, y0 + n[1]))):
+            wall = not yper and ((side == 0 and yr == 0) or (side == 1 and yr == npy - 1))
+            want = before[r][1:-1, lj, 1:-1] if wall else G[x0:x0 + n[0], wrap(gj, gy), :]
+            assert np.array_equal(a[1:-1, lj, 1:-1], want), (r, "y", side)
+        if xper and yper:       # fully periodic: the edge pads are the global diagonal points too
+            for li, gi in ((0, x0 - 1), (n[0] + 1, x0 + n[0])):
+                for lj, gj in ((0, y0 - 1), (n[1] + 1, y0 + n[1])):
+                    assert np.array_equal(a[li, lj, 1:-1], G[wrap(gi, gx), wrap(gj, gy), :]), (r, "edge")
