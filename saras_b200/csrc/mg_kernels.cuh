@@ -968,6 +968,9 @@ __global__ void __launch_bounds__(256) k_unpack_y2(double *__restrict__ A, const
 /* ------------------------------------------------------------------------------------------------ */
 /* every CTA calls this after its stores; the last one to arrive raises the flags */
 __device__ __forceinline__ void ipc_last_cta_signals(unsigned *counter, unsigned *flag_a, unsigned *flag_b, const unsigned epoch) {
+#ifdef MG_FENCE_ALL
+    __threadfence_system();
+#endif
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();         /* one fence per CTA: cumulative over the stores the barrier ordered before it */
@@ -1083,6 +1086,9 @@ __global__ void __launch_bounds__(1024) k_ipc_exchange_cta(double *A, const Leve
             if (send[0]) send[0][q] = A[mg_at(L, 1, j, k)];
             if (send[1]) send[1][q] = A[mg_at(L, L.nx - 2, j, k)];
         }
+#ifdef MG_FENCE_ALL
+        __threadfence_system();
+#endif
         __syncthreads();
         if (tid == 0) { __threadfence_system(); ipc_signal(sflag[0], epoch); ipc_signal(sflag[1], epoch); }
     }
@@ -1103,6 +1109,9 @@ __global__ void __launch_bounds__(1024) k_ipc_exchange_cta(double *A, const Leve
                 if (send[2]) send[2][q] = A[mg_at(L, i, 1, k)];
                 if (send[3]) send[3][q] = A[mg_at(L, i, L.ny - 2, k)];
             }
+#ifdef MG_FENCE_ALL
+            __threadfence_system();
+#endif
             __syncthreads();
             if (tid == 0) { __threadfence_system(); ipc_signal(sflag[2], epoch); ipc_signal(sflag[3], epoch); }
         }

@@ -96,6 +96,7 @@ struct GraphSlot {
     std::vector<ProfEntry> prof;    /* external event pairs recorded by the graph, re-read after every replay */
     long long launches;             /* kernels per replay */
     unsigned sites;                 /* peer-memory exchanges per replay */
+    bool stale_pads;                /* the cycle pushes level-0 halos: level 0's edge pads are stale after a replay (finalize_pads) */
 };
 
 struct sarasmg_solver_s {
@@ -170,6 +171,7 @@ struct sarasmg_solver_s {
     bool coarsen_legacy;        /* SARASMG_COARSEN_LEGACY: thread-per-coarse-point restriction kernel */
     bool prolong_legacy;        /* SARASMG_PROLONG_LEGACY: thread-per-fine-point prolongation kernel */
     double fuse_min_points;     /* fused residual + restriction on levels with at least this many core points */
+    bool no_zero_skip;          /* SARASMG_NO_ZEROSKIP: run the imposeBC of an all-zero coarse-level pressure array too */
     bool no_fuse;               /* SARASMG_NO_FUSE: computeResidual and coarsen as two passes on every level */
     bool no_pow2;               /* SARASMG_NO_POW2: keep the general exact-division path even when the divisors are powers of two (tests) */
     bool gs_legacy;             /* SARASMG_GS_LEGACY: one launch per hyperplane instead of the skewed single-launch sweep */
@@ -829,7 +831,7 @@ static int op_smooth(S *s, int count) {
     /* pressureData(l) == 0 everywhere, pads included (the memset of p:258 just ran): with homogeneous mirror / periodic faces
      * the first imposeBC copies zeros onto zeros on every rank -- skipped.  (Not under TEST_POISSON, whose odd mirror
      * would write -0.0.) */
-    const bool skip_first_bc = l < 32 && s->level_zero[l] && s->zeroBC && !s->d.test_poisson && count > 0;
+    const bool skip_first_bc = l < 32 && s->level_zero[l] && s->zeroBC && !s->d.test_poisson && count > 0 && !s->no_zero_skip;
     if (l < 32) s->level_zero[l] = false;
     for (int n = 0; n < count; ++n) {
         s->bucket = 2;
@@ -1441,6 +1443,8 @@ static int run_vcycle(S *s) {
         g = new GraphSlot();
         g->key = key; g->prof_key = pkey; g->exec = nullptr;
         const long long l0 = s->launches;
+        const bool stale_before = s->pads_stale;
+        s->pads_stale = false;
         s->capturing = true; s->cap_sites = 0; s->cap_prof = &g->prof;
         cudaError_t ce = cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal);
         int rc = (ce == cudaSuccess) ? op_vcycle(s, nullptr) : 1;
@@ -1459,6 +1463,8 @@ static int run_vcycle(S *s) {
         g->launches = s->launches - l0;
         s->launches = l0;
         g->sites = s->cap_sites;
+        g->stale_pads = s->pads_stale;          /* set by the captured op_smooth on level 0: a replay has to set it again */
+        s->pads_stale = stale_before;
         s->graphs.push_back(g);
     } else {
         /* the capture performed the host-side state changes of one cycle; a replay has to repeat them */
@@ -1482,6 +1488,7 @@ static int run_vcycle(S *s) {
         s->ipc_base_h = s->ipc_epoch;
     }
     CU(cudaGraphLaunch(g->exec, s->st));
+    if (g->stale_pads) s->pads_stale = true;
     s->ipc_epoch += g->sites;
     s->launches += g->launches;
     if (!g->prof.empty()) s->last_graph = g;
@@ -1632,6 +1639,7 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     s->prolong_legacy = getenv("SARASMG_PROLONG_LEGACY") != nullptr;
     s->coarsen_legacy = getenv("SARASMG_COARSEN_LEGACY") != nullptr;
     s->no_fuse = getenv("SARASMG_NO_FUSE") != nullptr;
+    s->no_zero_skip = getenv("SARASMG_NO_ZEROSKIP") != nullptr;
     s->fuse_min_points = getenv("SARASMG_FUSE_MIN") ? atof(getenv("SARASMG_FUSE_MIN")) : (getenv("SARASMG_TMA_MIN") ? 0.0 : 4.0e8);   /* tests that force the TMA kernels onto small grids get the fused pass too */
     for (int q = 0; q < 8; q++) s->user_ev[q] = nullptr;
     s->proj_ok = false; s->d_presP = nullptr;

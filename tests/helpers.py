@@ -54,7 +54,7 @@ def rel_linf(a, b):
     return max_abs(a - b) / den if den else max_abs(a - b)
 
 
-def check_natural_mean_field(o, p0_list, rhs_list, rank, p_got, p_ref_seq, what=""):
+def check_natural_mean_field(o, p0_list, rhs_list, rank, p_got, p_ref_seq, what="", got_mean=None):
     """Production mode with the DEVICE-computed RHS mean (poisson.cc:122-128).
 
     The reference forms the mean with one sequential fp64 sum; its rounding error (~sqrt(n) ulp, traversal-order
@@ -71,7 +71,8 @@ def check_natural_mean_field(o, p0_list, rhs_list, rank, p_got, p_ref_seq, what=
     o.mg_solve(pe, [a.copy() for a in rhs_list])
     exact_avg = o.last_global_avg()
     o.set_exact_mean(False)
-    assert np.array_equal(p_got, pe[rank]), "%s: natural mode differs from the exact-mean oracle by %g" % (what, max_abs(p_got - pe[rank]))
+    assert np.array_equal(p_got, pe[rank]), "%s: natural mode differs from the exact-mean oracle by %g (device mean %r, exact-mean oracle %r, sequential-sum oracle %r)" % (
+        what, max_abs(p_got - pe[rank]), got_mean, exact_avg, seq_avg)
     dev = rel_linf(p_got, p_ref_seq[rank])
     assert dev <= 1e-12 or (seq_avg != exact_avg and dev <= 1e-11), (what, dev, seq_avg, exact_avg)
     return dev

@@ -133,7 +133,8 @@ def run_gpu(rank, world, local):
     for case in cases:
         base = {k: v for k, v in case.items() if k not in ("name", "_env")}
         for key in ("SARASMG_COARSE_LEGACY", "SARASMG_HALO", "SARASMG_IPC_CTA_MAX", "SARASMG_GRAPH_MULTI", "SARASMG_TMA_MIN", "SARASMG_NO_PUSH"):
-            os.environ.pop(key, None)
+            if not os.environ.get("MP_KEEP_ENV"):       # debugging: keep what the caller exported
+                os.environ.pop(key, None)
         if case.get("_env"):
             key, val = case["_env"].split("=")
             os.environ[key] = val
@@ -199,6 +200,8 @@ def run_gpu(rank, world, local):
             p_ref = [a.copy() for a in p0]
             ref = o.mg_solve(p_ref, [a.copy() for a in rhs])
             modes = ["natural"] if cfg.get("test_poisson") else ["injected_mean", "natural"]
+            if os.environ.get("MP_NATURAL_FIRST"):
+                modes = modes[::-1]
             for mode in modes:
                 s.debug_set_rhs_mean(mode == "injected_mean", o.last_global_avg())
                 p = p0[rank].copy()
@@ -207,7 +210,7 @@ def run_gpu(rank, world, local):
                 assert np.array_equal(got["coarse_iters"], ref["coarse_iters"]), (what, got["coarse_iters"], ref["coarse_iters"])
                 np.testing.assert_allclose(got["residuals"], ref["residuals"], rtol=1e-10, atol=0)
                 if mode == "natural" and not cfg.get("test_poisson"):
-                    check_natural_mean_field(o, p0, rhs, rank, p, p_ref, what)
+                    check_natural_mean_field(o, p0, rhs, rank, p, p_ref, what, got_mean=s.last_rhs_mean())
                 else:
                     assert np.array_equal(p, p_ref[rank]), (what, mode, float(np.max(np.abs(p - p_ref[rank]))))
             # device-resident projection step across ranks: divergence -> mgSolve -> Pp.syncData (faces with
