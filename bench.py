@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument("--no-ttt", action="store_true", help="skip the time-to-tolerance solve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-index", type=int, default=0, help="grid index of the bounded CPU sample (0: the largest of 9 / 8 that fits the time budget)")
+    ap.add_argument("--no-proj", action="store_true", help="skip the device-resident projection-step leg (divergence -> mgSolve -> correction, SURVEY 8f-1/8f-2)")
+    ap.add_argument("--proj-multi", action="store_true", help="run the projection-step leg on N > 1 ranks as well")
     ap.add_argument("--no-gs", action="store_true", help="skip the Gauss-Seidel leg (the reference YAMLs' smoother) of the default Jacobi run")
     ap.add_argument("--_cpu-leg", dest="cpu_leg", default=None, help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -461,6 +463,46 @@ def run_b200(a):
             per_level_all.append(e)
     s.set_profile_max_level(1)
 
+    # projection step with every field resident: V.divergence -> mgRHS *= 1/dt -> mgSolve -> Pp.syncData ->
+    # P += Pp -> V -= dt grad(Pp) per step, nothing but the residual history crossing PCIe.  Reported beside `e2e`: it is what
+    # the hot path costs once hydro_d3's fields live on the device (uniform meshes only here: the metrics are 1/L).
+    def projection_leg():
+        n0 = dims[0]
+        shapes = s.proj_shapes()
+        L = 1.0
+        stag = [np.full(n0[d] + 2, 1.0 / L) for d in range(3)]
+        coll = [np.full(n0[d] + 1, 1.0 / L) for d in range(3)]
+        spacing = [1.0 / (1 << a.index)] * 3
+        s.proj_setup(stag, coll, spacing)
+        src = mgRHS.reshape(-1)             # random in [-1, 1): reused as the three velocity components
+        for which in (capi.PROJ_VX, capi.PROJ_VY, capi.PROJ_VZ):
+            cnt = int(np.prod(shapes[which]))
+            s.proj_upload(which, src[:cnt].reshape(shapes[which]))
+        dt = 0.01
+        s.proj_step(dt)                     # warm-up
+        barrier(); s.synchronize()
+        s.event_record(2)
+        s.proj_divergence(1.0 / dt)
+        s.event_record(3)
+        s.proj_correct(dt)
+        s.event_record(4)
+        ms_div, ms_cor = allmax(s.event_elapsed_ms(2, 3)), allmax(s.event_elapsed_ms(3, 4))
+        steps = max(2, min(a.steps, 3))
+        barrier(); s.synchronize()
+        s.event_record(5)
+        outs_p = [s.proj_step(dt) for _ in range(steps)]
+        s.event_record(6)
+        ms = allmax(s.event_elapsed_ms(5, 6)) / steps
+        s.synchronize(); barrier()
+        lups = sum(lups_per_solve(level_points, pre, post, o["coarse_iters"]) for o in outs_p) / steps
+        pts = level_points_local[0]
+        return dict(ms_per_step=ms, value=lups / (ms * 1e-3) / 1e9, unit=UNIT, cycles_per_step=[int(o["cycles"]) for o in outs_p],
+                    divergence_ms=ms_div, correction_ms=ms_cor,
+                    divergence_gbs=32.0 * pts / (ms_div * 1e-3) / 1e9, correction_gbs=80.0 * pts / (ms_cor * 1e-3) / 1e9,
+                    bytes_per_point="divergence 32 (read Vx, Vy, Vz, write mgRHS); correction 80 (copy Pp 16, P += Pp 24, three velocity updates 48 - 8 shared Pp read)",
+                    pcie_bytes_per_step=0,
+                    api="sarasmg_proj_step: vfield::divergence, mgRHS *= 1/dt, poisson::mgSolve, Pp.syncData, P += Pp, V -= dt grad(Pp) (hydro_d3.cc:326-362), all fields device-resident")
+
     # time to tolerance: the same hierarchy run until the reference's stagnation test |r_prev - r| < mgTolerance stops it
     def time_to_tolerance():
         s.set_vc_count(60)
@@ -528,6 +570,14 @@ def run_b200(a):
             cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"],
                        seconds=r["seconds_per_solve"], host_cores=r["host_cores"], single_core=r.get("single_core"))
 
+    # last: the projection leg overwrites the resident inputs of solve_resident
+    projection = None
+    if not a.no_proj and a.mesh == "uniform" and (world == 1 or a.proj_multi):   # N > 1 only on request: an exception on one rank would leave the others in a collective
+        try:
+            projection = projection_leg()
+        except Exception as e:            # extra information only: never take the bench line down
+            projection = dict(error=str(e)[:300])
+
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                     ms_per_step=ms_total / a.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
@@ -536,7 +586,7 @@ def run_b200(a):
                              coarse_iters=[int(v) for v in outs[-1]["coarse_iters"]], lups_per_step=lups_step,
                              fine_point_vcycles_per_s=level_points[0] * outs[-1]["cycles"] * a.steps / (ms_total * 1e-3)),
                     clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, per_level=per_level, per_level_all=per_level_all,
-                    gauss_seidel=gs, time_to_tolerance=ttt, cpu_baseline=cpu, breakdown=breakdown)
+                    gauss_seidel=gs, time_to_tolerance=ttt, cpu_baseline=cpu, breakdown=breakdown, projection_step=projection)
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:

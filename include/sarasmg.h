@@ -132,6 +132,29 @@ int sarasmg_proj_correct(sarasmg_handle h, double dt);                         /
 /* divergence -> mgSolve -> correction in one call; history arguments as in sarasmg_solve */
 int sarasmg_proj_step(sarasmg_handle h, double dt, int *cycles_done, double *residual_history, int *coarse_iters);
 
+/* ---- the implicit velocity solves of the time stepper, device-resident -------------------------------------
+ * hydro_d3::solveVx / solveVy / solveVz (src/solvers/hydro/hydro_d3.cc:370-533): Jacobi iterations of
+ * (1 - dt/(2 Re) Lap) V = nseRHS on the velocity component held by the projection entries above (sarasmg_proj_upload VX / VY /
+ * VZ), with hydro::imposeUBCs / VBCs / WBCs (hydro.cc:386-445) after every sweep -- syncData, then the wall objects of
+ * hydro::initVBC in the order left, right, front, back, top, bottom -- until max |residual| < cn_tolerance.  The result
+ * replaces the component on the device (the next sarasmg_proj_divergence reads it).  One rank; multigrid_d3 only. */
+enum { SARASMG_BC_NONE = 0, SARASMG_BC_DIRICHLET_CC, SARASMG_BC_DIRICHLET_FC, SARASMG_BC_NEUMANN, SARASMG_BC_PERIODIC_CC, SARASMG_BC_PERIODIC_FC };
+typedef struct {
+    double dt, Re, cn_tolerance;                        /* time step, inputParams.Re, inputParams.cnTolerance */
+    double hx, hy, hz;                                  /* hydro::setCoefficients, hydro.cc:223-241 (mesh.dXi, dEt, dZt ...) */
+    double hy2hz2, hz2hx2, hx2hy2, hx2hy2hz2;           /* ... and the host's pow() products */
+    const double *xix2_colloc, *ety2_colloc, *ztz2_colloc;      /* grid::xix2Colloc ..: n_d + 1 doubles, first entry is index -1 */
+    const double *xix2_staggr, *ety2_staggr, *ztz2_staggr;      /* grid::xix2Staggr ..: n_d + 2 doubles */
+    int bc_type[3][6];                                  /* [component][wall]: the boundary class of hydro::initVBC (SARASMG_BC_*), NONE on periodic x / y walls */
+    double bc_value[3][6];
+    long long max_iterations;                           /* hydro.cc:74: product of the collocated core sizes */
+} sarasmg_impl_desc;
+int sarasmg_impl_setup(sarasmg_handle h, const sarasmg_impl_desc *desc);
+int sarasmg_impl_upload_rhs(sarasmg_handle h, int component, const double *host);     /* nseRHS.Vx / Vy / Vz, layout of the component */
+int sarasmg_impl_bcs(sarasmg_handle h, int component);                                /* imposeUBCs / VBCs / WBCs alone */
+/* sweeps: Jacobi sweeps performed (iterCount + 1 of the reference); fails when max_iterations is exceeded (the reference aborts) */
+int sarasmg_impl_solve(sarasmg_handle h, int component, int *sweeps, double *max_error);
+
 /* TEST_POISSON epilogue (poisson.cc:153-204): max |analytic - pressureData(0)| over the core, all ranks */
 int sarasmg_analytic_deviation(sarasmg_handle h, double *max_dev);
 

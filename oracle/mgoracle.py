@@ -48,7 +48,7 @@ def _load(fast=False):
         return _LIBS[key]
     name = "libmgoracle_fast.so" if fast else "libmgoracle.so"
     path = os.path.join(_HERE, "_build", name)
-    srcs = [os.path.join(_HERE, f) for f in ("mg_oracle.c", "proj_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("mg_oracle.c", "proj_oracle.c", "impl_oracle.c")]
     if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(f) for f in srcs):
         build(fast)
     lib = C.CDLL(path)
@@ -91,10 +91,21 @@ def _load(fast=False):
     lib.projo_sync_one_rank.argtypes = [C.c_int] * 5 + [dp]
     lib.projo_correct.argtypes = [C.c_int] * 5 + [dp] * 8 + [C.c_double] * 4
     lib.projo_sync_multi.argtypes = [C.c_int] * 7 + [C.POINTER(dp)]
+    lib.implo_metric2.argtypes = [C.c_int, dp, dp]
+    lib.implo_impose_bcs.argtypes = [C.POINTER(ImploParams), C.c_int, dp]
+    lib.implo_solve.argtypes = [C.POINTER(ImploParams), C.c_int, dp, dp, dp]
+    lib.implo_solve.restype = C.c_int
     lib.projo_correct_nosync.argtypes = [C.c_int] * 3 + [dp] * 8 + [C.c_double] * 4
     lib.mgo_lup_count.argtypes = [vp]
     _LIBS[key] = lib
     return lib
+
+
+class ImploParams(C.Structure):
+    _fields_ = [("n", C.c_int * 3), ("per", C.c_int * 3), ("dt", C.c_double), ("Re", C.c_double), ("tol", C.c_double),
+                ("dXi", C.c_double), ("dEt", C.c_double), ("dZt", C.c_double),
+                ("m2c", C.POINTER(C.c_double) * 3), ("m2s", C.POINTER(C.c_double) * 3),
+                ("bc_type", C.c_int * 6), ("bc_value", C.c_double * 6)]
 
 
 DEFAULTS = dict(dim=3, test_poisson=0, xInd=5, yInd=5, zInd=5, npX=1, npY=1, xPer=0, yPer=0, zPer=0,
@@ -314,3 +325,55 @@ def proj_correct_nosync(n, pp, P, vx, vy, vz, coll, spacing, dt):
     """P += Pp; V -= dt grad(Pp) of one rank whose Pp is already synchronised; in place on P, vx, vy, vz"""
     _load().projo_correct_nosync(n[0], n[1], n[2], _dpp(pp), _dpp(P), _dpp(vx), _dpp(vy), _dpp(vz),
                                  _dpp(coll[0]), _dpp(coll[1]), _dpp(coll[2]), spacing[0], spacing[1], spacing[2], dt)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# implicit velocity solves (oracle/impl_oracle.c; SURVEY 8f-3)
+# ---------------------------------------------------------------------------------------------------------------------
+def impl_metrics2(o, rank=0):
+    """xi_x^2 .. at the collocated and the staggered points (grid.cc: pow(xi_x, 2.0) element by element)"""
+    stag, coll, _ = proj_metrics(o, rank)
+    lib = _load()
+    out = []
+    for arrs in (coll, stag):
+        sq = []
+        for a in arrs:
+            b = np.zeros_like(a)
+            lib.implo_metric2(a.size, _dpp(a), _dpp(b))
+            sq.append(b)
+        out.append(sq)
+    return out[0], out[1]
+
+
+class ImplOracle:
+    """hydro_d3::solveVx / Vy / Vz and imposeUBCs / VBCs / WBCs on one rank"""
+
+    def __init__(self, o, dt, Re, tol, bc_type, bc_value):
+        self.lib = _load()
+        self.n, _ = o.level_dims(0)
+        c = o.cfg
+        self.coll2, self.stag2 = impl_metrics2(o)
+        self.spacing = o.spacing()
+        self.params = []
+        for comp in range(3):
+            p = ImploParams()
+            p.n[:] = self.n
+            p.per[:] = [int(c["xPer"]), int(c["yPer"]), int(c["zPer"])]
+            p.dt, p.Re, p.tol = float(dt), float(Re), float(tol)
+            p.dXi, p.dEt, p.dZt = self.spacing
+            for d in range(3):
+                p.m2c[d] = _dpp(self.coll2[d])
+                p.m2s[d] = _dpp(self.stag2[d])
+            p.bc_type[:] = [int(v) for v in bc_type[comp]]
+            p.bc_value[:] = [float(v) for v in bc_value[comp]]
+            self.params.append(p)
+        self.max_iterations = (self.n[0] - 1) * (self.n[1] - 1) * (self.n[2] - 1)
+
+    def impose_bcs(self, comp, V):
+        self.lib.implo_impose_bcs(C.byref(self.params[comp]), comp, _dpp(V))
+
+    def solve(self, comp, V, rhs):
+        """in place on V; returns (sweeps, max_error); sweeps = -1 when the reference would abort"""
+        e = C.c_double(0.0)
+        n = self.lib.implo_solve(C.byref(self.params[comp]), comp, _dpp(V), _dpp(rhs), C.byref(e))
+        return n, e.value

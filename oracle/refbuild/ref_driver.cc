@@ -159,13 +159,16 @@ void rank_main(void *arg) {
         }
     }
     if (job->mode == 2 && job->proj_out) {
-        const blitz::Array<real, 1> *m[6] = {&gridData.xi_xStaggr, &gridData.et_yStaggr, &gridData.zt_zStaggr,
-                                              &gridData.xi_xColloc, &gridData.et_yColloc, &gridData.zt_zColloc};
+        const blitz::Array<real, 1> *m[12] = {&gridData.xi_xStaggr, &gridData.et_yStaggr, &gridData.zt_zStaggr,
+                                               &gridData.xi_xColloc, &gridData.et_yColloc, &gridData.zt_zColloc,
+                                               &gridData.xix2Staggr, &gridData.ety2Staggr, &gridData.ztz2Staggr,
+                                               &gridData.xix2Colloc, &gridData.ety2Colloc, &gridData.ztz2Colloc};
         size_t per_rank = 3;
-        for (int q = 0; q < 6; q++) per_rank += m[q]->size();
+        for (int q = 0; q < 12; q++) per_rank += m[q]->size();
         double *o = job->proj_out + (size_t)r * per_rank;
         for (int q = 0; q < 6; q++) for (int i = m[q]->lbound(0); i <= m[q]->ubound(0); i++) *o++ = (*m[q])(i);
         *o++ = gridData.dXi; *o++ = gridData.dEt; *o++ = gridData.dZt;
+        for (int q = 6; q < 12; q++) for (int i = m[q]->lbound(0); i <= m[q]->ubound(0); i++) *o++ = (*m[q])(i);
     }
     if (job->mode >= 1) return;
 

@@ -120,12 +120,13 @@ def setup_data(**kw):
 
 def proj_metrics(**kw):
     """First-derivative metrics of every rank as the reference's grid object holds them (grid.cc:370-519): per rank a dict with
-    xi_xStaggr, et_yStaggr, zt_zStaggr (index -1 .. n), xi_xColloc, et_yColloc, zt_zColloc (index -1 .. n-1) and (dXi, dEt, dZt)."""
+    xi_xStaggr, et_yStaggr, zt_zStaggr (index -1 .. n), xi_xColloc, et_yColloc, zt_zColloc (index -1 .. n-1), (dXi, dEt, dZt)
+    and the squared metrics xix2Staggr .. ztz2Colloc of the implicit solves."""
     cfg = _cfg(kw)
     lib = _load(cfg["dim"], cfg["test_poisson"], False)
     nr = cfg["npX"] * cfg["npY"]
     F = level0_extents(cfg)
-    per_rank = sum(F) + sum(f - 1 for f in F) + 3
+    per_rank = 2 * (sum(F) + sum(f - 1 for f in F)) + 3
     buf = np.zeros(nr * per_rank, dtype=np.float64)
     dp = C.POINTER(C.c_double)
     prm = MgoParams(**cfg)
@@ -143,5 +144,10 @@ def proj_metrics(**kw):
             d[name] = o[pos:pos + n].copy()
             pos += n
         d["spacing"] = tuple(o[pos:pos + 3])
+        pos += 3
+        for q, name in enumerate(["xix2Staggr", "ety2Staggr", "ztz2Staggr", "xix2Colloc", "ety2Colloc", "ztz2Colloc"]):
+            n = F[q % 3] - (1 if q >= 3 else 0)
+            d[name] = o[pos:pos + n].copy()
+            pos += n
         out.append(d)
     return out

@@ -35,7 +35,7 @@ def build_cuda(force=False, verbose=False, variant=None, defines=()):
         os.makedirs(os.path.join(LIBDIR, "variants"), exist_ok=True)
         out = os.path.join(LIBDIR, "variants", "libsarasmg_%s.so" % variant)
     srcs = [os.path.join(HERE, "csrc", "sarasmg.cu")]
-    deps = srcs + [os.path.join(HERE, "csrc", f) for f in ("mg_kernels.cuh", "gs_skew.cuh", "gs_strip.cuh", "mg_tma.cuh", "mg_fused.cuh", "proj_kernels.cuh")] + [os.path.join(ROOT, "include", "sarasmg.h")]
+    deps = srcs + [os.path.join(HERE, "csrc", f) for f in ("mg_kernels.cuh", "gs_skew.cuh", "gs_strip.cuh", "mg_tma.cuh", "mg_fused.cuh", "proj_kernels.cuh", "impl_kernels.cuh")] + [os.path.join(ROOT, "include", "sarasmg.h")]
     if force or _stale(out, deps):
         extra = os.environ.get("MG_NVCC_EXTRA", "").split() + list(defines)     # tuning experiments: -DMG_MARCH_MINB=5 ...
         cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs + ["-lnccl"]

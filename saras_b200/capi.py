@@ -46,6 +46,42 @@ class ProjDesc(C.Structure):
 
 
 PROJ_VX, PROJ_VY, PROJ_VZ, PROJ_P, PROJ_PP, PROJ_RHS = range(6)
+BC_NONE, BC_DIRICHLET_CC, BC_DIRICHLET_FC, BC_NEUMANN, BC_PERIODIC_CC, BC_PERIODIC_FC = range(6)
+
+
+class ImplDesc(C.Structure):
+    _fields_ = [("dt", C.c_double), ("Re", C.c_double), ("cn_tolerance", C.c_double),
+                ("hx", C.c_double), ("hy", C.c_double), ("hz", C.c_double),
+                ("hy2hz2", C.c_double), ("hz2hx2", C.c_double), ("hx2hy2", C.c_double), ("hx2hy2hz2", C.c_double),
+                ("xix2_colloc", _dp), ("ety2_colloc", _dp), ("ztz2_colloc", _dp),
+                ("xix2_staggr", _dp), ("ety2_staggr", _dp), ("ztz2_staggr", _dp),
+                ("bc_type", (C.c_int * 6) * 3), ("bc_value", (C.c_double * 6) * 3), ("max_iterations", C.c_longlong)]
+
+
+def velocity_bcs(x_per, y_per, z_per, prob_type=1):
+    """hydro::initVBC (src/solvers/hydro/hydro.cc:287-371): boundary class and value per [component][wall]"""
+    t = [[BC_NONE] * 6 for _ in range(3)]
+    v = [[0.0] * 6 for _ in range(3)]
+    if not x_per:
+        t[0][0], t[0][1] = BC_DIRICHLET_FC, BC_DIRICHLET_FC
+        t[1][0], t[1][1] = BC_DIRICHLET_CC, BC_DIRICHLET_CC
+        t[2][0], t[2][1] = BC_DIRICHLET_CC, BC_DIRICHLET_CC
+        if prob_type == 3:                  # inflow / outflow
+            v[0][0] = 1.0
+            t[0][1], t[1][1], t[2][1] = BC_NEUMANN, BC_NEUMANN, BC_NEUMANN
+    if not y_per:
+        t[0][2], t[0][3] = BC_DIRICHLET_CC, BC_DIRICHLET_CC
+        t[1][2], t[1][3] = BC_DIRICHLET_FC, BC_DIRICHLET_FC
+        t[2][2], t[2][3] = BC_DIRICHLET_CC, BC_DIRICHLET_CC
+    if z_per:
+        t[0][4] = t[0][5] = t[1][4] = t[1][5] = BC_PERIODIC_CC
+        t[2][4] = t[2][5] = BC_PERIODIC_FC
+    else:
+        t[0][4] = t[0][5] = t[1][4] = t[1][5] = BC_DIRICHLET_CC
+        t[2][4] = t[2][5] = BC_DIRICHLET_FC
+        if prob_type == 1:                  # lid-driven cavity: the lid moves with Vx = 1
+            v[0][5] = 1.0
+    return t, v
 
 _lib = None
 
@@ -60,6 +96,7 @@ SYMBOLS = [
     "sarasmg_last_solve_ms", "sarasmg_synchronize", "sarasmg_debug_set_rhs_mean",
     "sarasmg_set_profile_max_level", "sarasmg_event_record", "sarasmg_event_elapsed_ms", "sarasmg_host_register",
     "sarasmg_set_vc_count", "sarasmg_host_unregister", "sarasmg_set_smoother", "sarasmg_last_rhs_mean",
+    "sarasmg_impl_setup", "sarasmg_impl_upload_rhs", "sarasmg_impl_bcs", "sarasmg_impl_solve",
     "sarasmg_proj_setup", "sarasmg_proj_upload", "sarasmg_proj_download", "sarasmg_proj_divergence", "sarasmg_proj_correct", "sarasmg_proj_step",
 ]
 
@@ -120,6 +157,10 @@ def load():
     lib.sarasmg_proj_divergence.argtypes = [vp, C.c_double]
     lib.sarasmg_proj_correct.argtypes = [vp, C.c_double]
     lib.sarasmg_proj_step.argtypes = [vp, C.c_double, ip, _dp, ip]
+    lib.sarasmg_impl_setup.argtypes = [vp, C.POINTER(ImplDesc)]
+    lib.sarasmg_impl_upload_rhs.argtypes = [vp, C.c_int, _dp]
+    lib.sarasmg_impl_bcs.argtypes = [vp, C.c_int]
+    lib.sarasmg_impl_solve.argtypes = [vp, C.c_int, ip, _dp]
     _lib = lib
     return lib
 
@@ -388,6 +429,40 @@ class Solver:
         hist, iters, cyc = self._hist()
         self._check(self.lib.sarasmg_proj_step(self.h, float(dt), C.byref(cyc), _ptr(hist), iters.ctypes.data_as(C.POINTER(C.c_int))))
         return dict(cycles=cyc.value, residuals=hist[:cyc.value].copy(), coarse_iters=iters[:cyc.value].copy())
+
+    # -- implicit velocity solves ---------------------------------------------------------
+    def impl_setup(self, dt, Re, tol, spacing, colloc2, staggr2, bc_type, bc_value, max_iterations):
+        """colloc2 / staggr2: xi_x^2, et_y^2, zt_z^2 at collocated / staggered points (first entry = index -1)"""
+        d = ImplDesc()
+        d.dt, d.Re, d.cn_tolerance = float(dt), float(Re), float(tol)
+        hx, hy, hz = [float(v) for v in spacing]
+        d.hx, d.hy, d.hz = hx, hy, hz
+        d.hz2hx2 = pow(hz, 2.0) * pow(hx, 2.0)          # hydro::setCoefficients, hydro.cc:223-241 (Python's pow is C's pow)
+        d.hx2hy2 = pow(hx, 2.0) * pow(hy, 2.0)
+        d.hy2hz2 = pow(hy, 2.0) * pow(hz, 2.0)
+        d.hx2hy2hz2 = pow(hx, 2.0) * pow(hy, 2.0) * pow(hz, 2.0)
+        self._impl_keep = [_f64(a) for a in list(colloc2) + list(staggr2)]
+        for name, a in zip(("xix2_colloc", "ety2_colloc", "ztz2_colloc", "xix2_staggr", "ety2_staggr", "ztz2_staggr"), self._impl_keep):
+            setattr(d, name, _ptr(a))
+        for c in range(3):
+            for w in range(6):
+                d.bc_type[c][w] = int(bc_type[c][w])
+                d.bc_value[c][w] = float(bc_value[c][w])
+        d.max_iterations = int(max_iterations)
+        self._check(self.lib.sarasmg_impl_setup(self.h, C.byref(d)))
+
+    def impl_upload_rhs(self, comp, a):
+        a = _f64(a)
+        assert a.shape == self.proj_shapes()[comp]
+        self._check(self.lib.sarasmg_impl_upload_rhs(self.h, comp, _ptr(a)))
+
+    def impl_bcs(self, comp):
+        self._check(self.lib.sarasmg_impl_bcs(self.h, comp))
+
+    def impl_solve(self, comp):
+        n, e = C.c_int(0), C.c_double(0.0)
+        self._check(self.lib.sarasmg_impl_solve(self.h, comp, C.byref(n), C.byref(e)))
+        return n.value, e.value
 
     def last_rhs_mean(self):
         v = C.c_double(0.0)

@@ -20,6 +20,7 @@
 #include "mg_tma.cuh"
 #include "mg_fused.cuh"
 #include "proj_kernels.cuh"
+#include "impl_kernels.cuh"
 
 #include <nccl.h>
 
@@ -184,6 +185,12 @@ struct sarasmg_solver_s {
     size_t vel_elems[3];
     double *d_presP;            /* P in the pitched level-0 layout */
     double *d_pmet[6];          /* xi_xStaggr, et_yStaggr, zt_zStaggr, xi_xColloc, et_yColloc, zt_zColloc */
+    /* implicit velocity solves */
+    bool impl_ok;
+    sarasmg_impl_desc impl;
+    double *d_impl_met[6];      /* xix2Colloc, ety2Colloc, ztz2Colloc, xix2Staggr, ety2Staggr, ztz2Staggr */
+    double *d_nse[3];           /* nseRHS components */
+    double *d_guess[3];         /* guessedVelocity components (ping-pong partners of d_vel) */
     double *d_psync[2];         /* send / receive buffer of Pp.syncData() between ranks */
     ProjSyncPlan psync;
     int edge_ranks[4];          /* parallel.cc:124-129: always the periodic wrap, never nulled by checkPeriodic */
@@ -1646,6 +1653,9 @@ static int create_impl(const sarasmg_desc *desc, S *s) {
     for (int q = 0; q < 3; q++) { s->d_vel[q] = nullptr; s->vel_elems[q] = 0; }
     for (int q = 0; q < 6; q++) s->d_pmet[q] = nullptr;
     s->d_psync[0] = s->d_psync[1] = nullptr;
+    s->impl_ok = false;
+    for (int q = 0; q < 6; q++) s->d_impl_met[q] = nullptr;
+    for (int q = 0; q < 3; q++) { s->d_nse[q] = nullptr; s->d_guess[q] = nullptr; }
     memset(s->prof_ms, 0, sizeof(s->prof_ms));
     memset(s->prof_n, 0, sizeof(s->prof_n));
     for (int q = 0; q < 3; q++) s->d_wall[q] = nullptr;
@@ -1873,6 +1883,8 @@ int sarasmg_destroy(sarasmg_handle s) {
     for (int q = 0; q < 3; q++) cudaFree(s->d_vel[q]);
     for (int q = 0; q < 6; q++) cudaFree(s->d_pmet[q]);
     cudaFree(s->d_psync[0]); cudaFree(s->d_psync[1]);
+    for (int q = 0; q < 6; q++) cudaFree(s->d_impl_met[q]);
+    for (int q = 0; q < 3; q++) { cudaFree(s->d_nse[q]); cudaFree(s->d_guess[q]); }
     cudaFree(s->d_presP);
     for (auto &e : s->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto &e : s->ev_pool) cudaEventDestroy(e);
@@ -2112,6 +2124,136 @@ int sarasmg_proj_step(sarasmg_handle s, double dt, int *cycles_done, double *res
     TRY(solve_core(s, s->d_in_p, s->d_in_rhs, cycles_done, residual_history, coarse_iters));
     TRY(proj_correct(s, dt));
     CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+/* ---- implicit velocity solves ---- */
+static ImplGeom impl_geom(const S *s, int comp) {
+    ImplGeom g;
+    const LevelView &v0 = s->lev[0].v;
+    const int n[3] = {v0.nx, v0.ny, v0.nz};
+    const int per[3] = {s->d.x_per, s->d.y_per, s->d.z_per};
+    for (int d = 0; d < 3; d++) {
+        g.stag[d] = (d != comp) ? 1 : 0;
+        g.cs[d] = g.stag[d] ? n[d] : n[d] - 1;
+        g.ext[d] = g.cs[d] + 2;
+        const int cut = (g.stag[d] && !per[d]) ? 1 : 0;                /* field.cc:206-219 on one rank */
+        g.lb[d] = cut; g.ub[d] = g.cs[d] - 1 - cut;
+    }
+    g.mx = s->d_impl_met[g.stag[0] ? 3 : 0] + 1; g.my = s->d_impl_met[g.stag[1] ? 4 : 1] + 1; g.mz = s->d_impl_met[g.stag[2] ? 5 : 2] + 1;
+    return g;
+}
+static ImplCoef impl_coef(const S *s) {
+    const sarasmg_impl_desc &d = s->impl;
+    ImplCoef c;
+    c.hy2hz2 = d.hy2hz2; c.hz2hx2 = d.hz2hx2; c.hx2hy2 = d.hx2hy2; c.hx2hy2hz2 = d.hx2hy2hz2;
+    c.hx = d.hx; c.hy = d.hy; c.hz = d.hz; c.dt = d.dt; c.Re = d.Re; c.inverseRe = 1.0 / d.Re;     /* hydro.cc:65 */
+    return c;
+}
+int sarasmg_impl_setup(sarasmg_handle s, const sarasmg_impl_desc *d) {
+    if (!s || !d) return set_err("sarasmg_impl_setup: null argument");
+    if (!s->proj_ok) return set_err("sarasmg_impl_setup: call sarasmg_proj_setup first (the velocity components live there)");
+    if (s->d.n_proc != 1) return set_err("sarasmg_impl_setup: one rank only for now");
+    if (!d->xix2_colloc || !d->ety2_colloc || !d->ztz2_colloc || !d->xix2_staggr || !d->ety2_staggr || !d->ztz2_staggr)
+        return set_err("sarasmg_impl_setup: null metric array");
+    if (!(d->Re > 0.0) || !(d->dt > 0.0)) return set_err("sarasmg_impl_setup: dt and Re must be positive");
+    CU(cudaSetDevice(s->d.device));
+    const LevelView &v0 = s->lev[0].v;
+    const double *src[6] = {d->xix2_colloc, d->ety2_colloc, d->ztz2_colloc, d->xix2_staggr, d->ety2_staggr, d->ztz2_staggr};
+    const int len[6] = {v0.nx + 1, v0.ny + 1, v0.nz + 1, v0.nx + 2, v0.ny + 2, v0.nz + 2};
+    for (int q = 0; q < 6; q++) {
+        if (!s->d_impl_met[q]) CU(cudaMalloc(&s->d_impl_met[q], sizeof(double) * len[q]));
+        CU(cudaMemcpyAsync(s->d_impl_met[q], src[q], sizeof(double) * len[q], cudaMemcpyHostToDevice, s->st));
+    }
+    for (int c = 0; c < 3; c++) {
+        if (!s->d_nse[c]) CU(cudaMalloc(&s->d_nse[c], sizeof(double) * s->vel_elems[c]));
+        if (!s->d_guess[c]) CU(cudaMalloc(&s->d_guess[c], sizeof(double) * s->vel_elems[c]));
+        CU(cudaMemsetAsync(s->d_nse[c], 0, sizeof(double) * s->vel_elems[c], s->st));
+    }
+    CU(cudaStreamSynchronize(s->st));
+    s->impl = *d;
+    s->impl.xix2_colloc = s->impl.ety2_colloc = s->impl.ztz2_colloc = s->impl.xix2_staggr = s->impl.ety2_staggr = s->impl.ztz2_staggr = nullptr;
+    s->impl_ok = true;
+    return 0;
+}
+int sarasmg_impl_upload_rhs(sarasmg_handle s, int comp, const double *host) {
+    if (!s || !host || comp < 0 || comp > 2) return set_err("sarasmg_impl_upload_rhs: bad argument");
+    if (!s->impl_ok) return set_err("sarasmg_impl_upload_rhs: call sarasmg_impl_setup first");
+    CU(cudaSetDevice(s->d.device));
+    CU(cudaMemcpyAsync(s->d_nse[comp], host, sizeof(double) * s->vel_elems[comp], cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+/* imposeUBCs / VBCs / WBCs (hydro.cc:386-445) on one rank */
+static int impl_bcs(S *s, int comp, double *F) {
+    const ImplGeom g = impl_geom(s, comp);
+    const int xper = s->d.x_per ? 1 : 0, yper = s->d.y_per ? 1 : 0;
+    if (xper || yper) {
+        const long long cnt = (xper ? (long long)g.cs[1] * g.cs[2] : 0) + (yper ? (long long)g.cs[0] * g.cs[2] : 0);
+        k_impl_sync_faces<<<face_blocks(cnt), 256, 0, s->st>>>(F, g, xper, yper);
+        TRY(kcheck(s, "k_impl_sync_faces"));
+    }
+    k_impl_sync_edges<<<cdiv(g.cs[2], 256), 256, 0, s->st>>>(F, g);
+    TRY(kcheck(s, "k_impl_sync_edges"));
+    const int order[6] = {0, 1, 2, 3, 5, 4};
+    for (int q = 0; q < 6; q++) {
+        const int w = order[q], ax = w / 2, hi = w & 1;
+        const int t = s->impl.bc_type[comp][w];
+        if (t == SARASMG_BC_NONE) continue;
+        const int wall_lo = g.lb[ax] - 1, wall_hi = g.ub[ax] + 1;      /* field.cc:270-285 */
+        const int dst = hi ? wall_hi : wall_lo;
+        int src = dst + (hi ? -1 : 1);                                 /* shiftVal, boundary.cc:55-84 */
+        if (t == SARASMG_BC_PERIODIC_CC) src = hi ? wall_lo + 2 : wall_hi - 2;
+        if (t == SARASMG_BC_PERIODIC_FC) src = hi ? wall_lo + 1 : wall_hi - 1;
+        const int a1 = (ax == 0) ? 1 : 0, a2 = (ax == 2) ? 1 : 2;
+        k_impl_plane<<<face_blocks((long long)g.ext[a1] * g.ext[a2]), 256, 0, s->st>>>(F, g, ax, dst, src, t, s->impl.bc_value[comp][w]);
+        TRY(kcheck(s, "k_impl_plane"));
+    }
+    return 0;
+}
+int sarasmg_impl_bcs(sarasmg_handle s, int comp) {
+    if (!s || comp < 0 || comp > 2) return set_err("sarasmg_impl_bcs: bad argument");
+    if (!s->impl_ok) return set_err("sarasmg_impl_bcs: call sarasmg_impl_setup first");
+    CU(cudaSetDevice(s->d.device));
+    TRY(impl_bcs(s, comp, s->d_vel[comp]));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+int sarasmg_impl_solve(sarasmg_handle s, int comp, int *sweeps, double *max_error) {
+    if (!s || comp < 0 || comp > 2) return set_err("sarasmg_impl_solve: bad argument");
+    if (!s->impl_ok) return set_err("sarasmg_impl_solve: call sarasmg_impl_setup first");
+    CU(cudaSetDevice(s->d.device));
+    const ImplGeom g = impl_geom(s, comp);
+    const ImplCoef c = impl_coef(s);
+    const dim3 gs(cdiv(g.ext[2], 256), g.ext[1], g.ext[0]);
+    const int bn[3] = {g.ub[0] - g.lb[0] + 1, g.ub[1] - g.lb[1] + 1, g.ub[2] - g.lb[2] + 1};
+    if (bn[0] < 1 || bn[1] < 1 || bn[2] < 1) return set_err("sarasmg_impl_solve: empty bulk");
+    const dim3 ge(cdiv(bn[2], 256), bn[1], bn[0]);
+    const size_t nb = (size_t)ge.x * ge.y * ge.z;
+    TRY(ensure_part(s, nb + 16));
+    long long iterCount = 0;
+    double maxError = 0.0;
+    for (;;) {
+        k_impl_sweep<<<gs, 256, 0, s->st>>>(s->d_vel[comp], s->d_nse[comp], s->d_guess[comp], g, c);
+        TRY(kcheck(s, "k_impl_sweep"));
+        std::swap(s->d_vel[comp], s->d_guess[comp]);                    /* V.Vx.F = guessedVelocity.Vx (every entry of it was just written) */
+        TRY(impl_bcs(s, comp, s->d_vel[comp]));
+        k_impl_error<<<ge, 256, 0, s->st>>>(s->d_vel[comp], s->d_nse[comp], g, c, s->d_part);
+        TRY(kcheck(s, "k_impl_error"));
+        k_reduce_final<<<1, 1024, 0, s->st>>>(s->d_part, (int)nb, 1, 1u, s->d_scal);
+        TRY(kcheck(s, "k_reduce_final"));
+        CU(cudaMemcpyAsync(s->h_scal, s->d_scal, sizeof(double), cudaMemcpyDeviceToHost, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        maxError = std::max(s->h_scal[0], 0.0);                         /* vxMax runs over the whole array, whose non-bulk entries are 0 */
+        if (maxError < s->impl.cn_tolerance) break;
+        iterCount += 1;
+        if (iterCount > s->impl.max_iterations) {
+            if (max_error) *max_error = maxError;
+            return set_err("sarasmg_impl_solve: Jacobi iterations for solution of V%c not converging (the reference aborts here, hydro_d3.cc:415-421)", "xyz"[comp]);
+        }
+    }
+    if (sweeps) *sweeps = (int)(iterCount + 1);
+    if (max_error) *max_error = maxError;
     return 0;
 }
 
