@@ -12,10 +12,12 @@
  *   mpidata::syncData on one rank               lib/parallel/mpidata.cc:82-306 (collocated directions send plane 0 / n-1, staggered 1 / n-2)
  *   plainvf::vxMax                              lib/field/plainvf.h:97-105 (max over the WHOLE array; its non-bulk entries stay 0)
  *
- * PARITY UNPINNED: lib/field, lib/boundary and src/solvers need Blitz++ expression templates the stand-in headers of
- * oracle/refbuild do not provide, so the reference's own time stepper cannot be compiled here.  The loops follow the cited
- * statements operand by operand (Blitz and C++ evaluate `a*b*(c+d)` left to right) but have not been checked against an
- * execution of the reference.  One rank only.
+ * PINNED against an execution of the reference itself: tests/test_oracle_vs_timestepper.py runs the reference's own
+ * hydro_d3::solveVx / solveVy / solveVz and hydro::imposeUBCs / VBCs / WBCs (oracle/_ref/libsarasts_d3.so: the unmodified
+ * sources compiled by oracle/refbuild/Makefile, driven by oracle/refbuild/ts_driver.cc) and requires this file to reproduce
+ * the resulting velocity fields BIT FOR BIT -- lid-driven cavity, channel, fully periodic and inflow / outflow boundary sets,
+ * uniform and tanh meshes, alone and chained with the projection step.  The squared metrics are pinned against the reference's
+ * grid object (tests/test_impl_oracle.py).  One rank only.
  *
  * A velocity component is a Blitz array with base index -1, z fastest: extent of a direction = core size + 2, where the core
  * has n points if the component is staggered (cell-centred) there and n - 1 if it is collocated (face-centred): Vx is

@@ -10,13 +10,13 @@
  *   plainsf::gradient                   lib/field/plainsf.h:92-98          + `pressureGradient *= dt; V -= pressureGradient`  hydro_d3.cc:360-362
  *   collocated metric xi_xColloc        lib/grid/grid.cc:370-422 (uniform), 442-519 (tanh)
  *
- * PIN STATUS.  The metric restatements (projo_colloc_metric / projo_staggr_metric) are pinned bit for bit against the
- * reference's own grid object (oracle/_ref, grid.cc compiled unmodified; tests/test_proj_oracle.py, uniform / tanh, 1-4 ranks).
- * PARITY UNPINNED for the three field loops (divergence, syncData, correction): lib/field needs Blitz++ tensor-index
- * expressions and stencil operators that the stand-in headers of oracle/refbuild do not provide, so the reference's own
- * field library cannot be compiled here; these loops follow the cited statements operand by operand (Blitz evaluates
- * `a(i)*(F1 - F2)/d` left to right) and are cross-checked against an independent numpy statement of the same expressions,
- * but have not been checked against an execution of the reference.
+ * PINNED against an execution of the reference itself.  oracle/_ref/libsarasts_d3.so is the reference's UNMODIFIED
+ * src/solvers/hydro, lib/field, lib/boundary, lib/parallel/mpidata.cc ... compiled by oracle/refbuild/Makefile (stand-in Blitz /
+ * MPI / yaml-cpp headers; oracle/refbuild/ts_driver.cc calls the statements cited above the way hydro_d3::timeAdvance does, on
+ * CPU thread-ranks).  tests/test_oracle_vs_timestepper.py requires every function of this file to reproduce it BIT FOR BIT:
+ * divergence, syncData + correction on 1, 2x1, 2x2, 4x2 and 1x2 ranks (uniform / tanh, periodic / walls), and the whole tail
+ * of timeAdvance chained with the multigrid and the implicit-solve oracles.  The metric restatements are pinned against the
+ * reference's grid object as well (tests/test_proj_oracle.py).
  *
  * Array layouts are the reference's Blitz arrays, base index -1 in every direction, z fastest (lib/field/field.cc:66-105):
  *   staggered scalar (P, Pp, mgRHS)  (nx+2, ny+2, nz+2);  Vx (nx+1, ny+2, nz+2);  Vy (nx+2, ny+1, nz+2);  Vz (nx+2, ny+2, nz+1)

@@ -1,0 +1,149 @@
+/*
+ * ts_driver.cc -- TEST INFRASTRUCTURE: runs pieces of the REFERENCE's own time stepper on CPU thread-ranks, so that the oracles
+ * of the projection step (oracle/proj_oracle.c) and of the implicit velocity solves (oracle/impl_oracle.c) are pinned against
+ * an execution of the reference itself.
+ *
+ * Linked into oracle/_ref/libsarasts_d3.so with the reference's UNMODIFIED sources, compiled from where they lie under
+ * /root/reference: src/solvers/hydro/{hydro,hydro_d3}.cc, lib/field/*.cc, lib/boundary/*.cc (but hotPlateCC.cc, a scalar-solver
+ * class), lib/force/*.cc, lib/initial/*.cc, lib/io/{parser,tseries}.cc, lib/parallel/{parallel,mpidata}.cc, lib/grid/grid.cc,
+ * lib/poisson/*.cc -- against the stand-in Blitz / MPI / yaml-cpp headers of saras_b200/host/compat.  The HDF5-backed classes
+ * (writer, reader, probes) are not built: standin_ts/hdf5.h lets their headers parse, and this file defines the members the
+ * time stepper references as do-nothing functions (none is called here: no solvePDE, no restart).
+ *
+ * What runs is the reference's code, called the way hydro_d3::timeAdvance calls it (src/solvers/hydro/hydro_d3.cc):
+ *   mode 0  V.divergence(mgRHS, P); mgRHS *= 1.0/dt;                                                    :326-327
+ *   mode 1  Pp.syncData(); P += Pp; Pp.gradient(pressureGradient, V); pressureGradient *= dt; V -= pressureGradient;   :347-362
+ *   mode 2  imposeUBCs(); imposeVBCs(); imposeWBCs();                                                   :364-366
+ *   mode 3  solveVx(); solveVy(); solveVz();                                                            :306-316
+ *   mode 4  modes 3, 0, mgSolve, 1, 2 in sequence: the tail of timeAdvance from nseRHS on               :303-366
+ * Fields go in and out as the padded Blitz arrays of every rank.  Ranks are threads (mpi-lite).
+ */
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <unistd.h>
+
+#define protected public            /* the pieces of hydro_d3 called below are protected members; the sources stay unmodified */
+#define private public
+#include "hydro.h"
+#undef protected
+#undef private
+
+/* ---- do-nothing members of the HDF5-backed classes (see the header comment) ---- */
+writer::writer(const grid &mesh, std::vector<field> &wFields) : mesh(mesh), wFields(wFields) {}
+void writer::writeTarang(real) {}
+void writer::writeSolution(real) {}
+void writer::writeRestart(real) {}
+writer::~writer() {}
+reader::reader(const grid &mesh, std::vector<field> &rFields) : mesh(mesh), rFields(rFields) {}
+real reader::readData() { return 0.0; }
+reader::~reader() {}
+probes::probes(const grid &mesh, std::vector<field> &pFields) : mesh(mesh), pFields(pFields), numFields(0) {}
+void probes::probeData(real) {}
+probes::~probes() {}
+
+extern "C" {
+
+typedef struct {
+    int xInd, yInd, zInd, npX, npY, xPer, yPer, zPer, xGrid, yGrid, zGrid;
+    double betaX, betaY, betaZ, Lx, Ly, Lz;
+    int vcDepth, vcCount, preSmooth, postSmooth, gsSmooth, resType;
+    double mgTolerance;
+    int probType;           /* "Problem Type": 1 lid-driven cavity, 3 inflow / outflow, 4 channel, ... (hydro.cc:287-371) */
+    double Re, dt, cnTolerance;
+} ts_params;
+
+/* per rank: Vx, Vy, Vz, P, Pp, mgRHS, nseRHS.Vx, nseRHS.Vy, nseRHS.Vz (any may be NULL: left as the constructor set it) */
+typedef struct { double *f[9]; } ts_rank_fields;
+
+}
+
+namespace {
+
+struct Job { const ts_params *prm; ts_rank_fields *flds; int mode; int status; };
+
+void write_yaml(const ts_params &p, const std::string &dir) {
+    std::string cmd = "mkdir -p " + dir + "/input";
+    if (system(cmd.c_str()) != 0) fprintf(stderr, "ts_driver: cannot create %s\n", dir.c_str());
+    std::ofstream f((dir + "/input/parameters.yaml").c_str());
+    char dom[4] = {p.xPer ? 'P' : 'N', p.yPer ? 'P' : 'N', p.zPer ? 'P' : 'N', 0};
+    char mesh[4] = {p.xGrid == 2 ? 'D' : 'U', p.yGrid == 2 ? 'D' : 'U', p.zGrid == 2 ? 'D' : 'U', 0};
+    f.precision(17);
+    f << "\"Program\":\n"
+      << "    \"Problem Type\": " << p.probType << "\n    \"Initial Condition\": 0\n    \"Domain Type\": \"" << dom << "\"\n    \"RBC Type\": 1\n"
+      << "    \"Reynolds Number\": " << p.Re << "\n    \"Rossby Number\": 12\n    \"Rayleigh Number\": 10000\n    \"Prandtl Number\": 0.71\n"
+      << "    \"Taylor Number\": 0.0\n    \"X Length\": " << p.Lx << "\n    \"Y Length\": " << p.Ly << "\n    \"Z Length\": " << p.Lz << "\n"
+      << "    \"Heating Plate\": false\n    \"Plate Radius\": 0.25\n    \"Force\": 0\n"
+      << "\"Mesh\":\n    \"Mesh Type\": \"" << mesh << "\"\n    \"X Beta\": " << p.betaX << "\n    \"Y Beta\": " << p.betaY << "\n    \"Z Beta\": " << p.betaZ << "\n"
+      << "    \"X Index\": " << p.xInd << "\n    \"Y Index\": " << p.yInd << "\n    \"Z Index\": " << p.zInd << "\n"
+      << "\"Parallel\":\n    \"Number of OMP threads\": 1\n    \"X Number of Procs\": " << p.npX << "\n    \"Y Number of Procs\": " << p.npY << "\n"
+      << "\"Solver\":\n    \"Differentiation Scheme\": 1\n    \"Integration Scheme\": 1\n    \"Solve Tolerance\": " << p.cnTolerance << "\n    \"Restart Run\": false\n"
+      << "    \"Use CFL Condition\": false\n    \"Courant Number\": 0.1\n    \"Time-Step\": " << p.dt << "\n    \"Final Time\": " << p.dt << "\n    \"I/O Count\": 1\n"
+      << "    \"Solution Format\": 1\n    \"Solution Write Interval\": 1.0\n    \"Restart Write Interval\": 1.0\n    \"Record Probes\": false\n"
+      << "    \"Probe Time Interval\": 0.1\n    \"Probes\": >\n        [5, 5, 5]\n"
+      << "\"Multigrid\":\n    \"V-Cycle Depth\": " << p.vcDepth << "\n    \"V-Cycle Count\": " << p.vcCount << "\n    \"Solve Tolerance\": " << p.mgTolerance << "\n"
+      << "    \"Smoothing Method\": " << p.gsSmooth << "\n    \"Pre-Smoothing Count\": " << p.preSmooth << "\n    \"Post-Smoothing Count\": " << p.postSmooth << "\n"
+      << "    \"Residual Type\": " << p.resType << "\n    \"Print Residual\": false\n";
+}
+
+void put(blitz::Array<real, 3> &A, const double *src) { if (src) memcpy(A.dataFirst(), src, A.size() * sizeof(double)); }
+void get(const blitz::Array<real, 3> &A, double *dst) { if (dst) memcpy(dst, A.dataFirst(), A.size() * sizeof(double)); }
+
+void rank_main(void *arg) {
+    Job *job = (Job *)arg;
+    const ts_params &p = *job->prm;
+    parser inputParams;                          /* reads ./input/parameters.yaml */
+    parallel mpi(inputParams);
+    grid gridData(inputParams, mpi);
+    hydro_d3 H(gridData, inputParams, mpi);      /* P = 1, zero initial condition, checkPeriodic, initVBC, imposeU/V/WBCs */
+    H.dt = p.dt;                                 /* hydro_d3::solvePDE sets dt = inputParams.tStp (hydro_d3.cc:157); set here as no solvePDE runs */
+    ts_rank_fields &F = job->flds[mpi.rank];
+    put(H.V.Vx.F, F.f[0]); put(H.V.Vy.F, F.f[1]); put(H.V.Vz.F, F.f[2]);
+    put(H.P.F.F, F.f[3]); put(H.Pp.F, F.f[4]); put(H.mgRHS.F, F.f[5]);
+    put(H.nseRHS.Vx, F.f[6]); put(H.nseRHS.Vy, F.f[7]); put(H.nseRHS.Vz, F.f[8]);
+    const int m = job->mode;
+    if (m == 3 || m == 4) { H.solveVx(); H.solveVy(); H.solveVz(); }
+    if (m == 0 || m == 4) { H.V.divergence(H.mgRHS, H.P); H.mgRHS *= 1.0 / H.dt; }
+    if (m == 4 || m == 5) H.mgSolver.mgSolve(H.Pp, H.mgRHS);      /* mode 5: mgSolve alone (debugging aid) */
+    if (m == 1 || m == 4) {
+        H.Pp.syncData();
+        H.P += H.Pp;
+        H.Pp.gradient(H.pressureGradient, H.V);
+        H.pressureGradient *= H.dt;
+        H.V -= H.pressureGradient;
+    }
+    if (m == 2 || m == 4) { H.imposeUBCs(); H.imposeVBCs(); H.imposeWBCs(); }
+    get(H.V.Vx.F, F.f[0]); get(H.V.Vy.F, F.f[1]); get(H.V.Vz.F, F.f[2]);
+    get(H.P.F.F, F.f[3]); get(H.Pp.F, F.f[4]); get(H.mgRHS.F, F.f[5]);
+}
+
+}  // namespace
+
+extern "C" {
+
+/* padded extents of the nine fields of one rank, in the order of ts_rank_fields (9 x 3 ints) */
+void sarasts_extents(const ts_params *p, int *out) {
+    const int n[3] = {(1 << p->xInd) / p->npX + 1, (1 << p->yInd) / p->npY + 1, (1 << p->zInd) + 1};
+    const int sc[3] = {n[0] + 2, n[1] + 2, n[2] + 2};
+    const int vx[3] = {n[0] + 1, n[1] + 2, n[2] + 2}, vy[3] = {n[0] + 2, n[1] + 1, n[2] + 2}, vz[3] = {n[0] + 2, n[1] + 2, n[2] + 1};
+    const int *all[9] = {vx, vy, vz, sc, sc, sc, vx, vy, vz};
+    for (int q = 0; q < 9; q++) for (int d = 0; d < 3; d++) out[3 * q + d] = all[q][d];
+}
+
+int sarasts_run(const char *workdir, const ts_params *prm, ts_rank_fields *flds, int mode) {
+    write_yaml(*prm, workdir);
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof(cwd))) return -1;
+    if (chdir(workdir) != 0) return -1;
+    std::ostringstream captured;
+    std::streambuf *old = std::cout.rdbuf(captured.rdbuf());
+    Job job = {prm, flds, mode, 0};
+    saras_mpi_run(prm->npX * prm->npY, rank_main, &job);
+    std::cout.rdbuf(old);
+    if (chdir(cwd) != 0) return -1;
+    return job.status;
+}
+
+}

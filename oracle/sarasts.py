@@ -1,0 +1,78 @@
+"""ctypes wrapper of oracle/_ref/libsarasts_d3.so: pieces of the REFERENCE's own time stepper (hydro_d3, lib/field, lib/boundary,
+mpidata; unmodified sources compiled by oracle/refbuild/Makefile) run on CPU thread-ranks.  TEST INFRASTRUCTURE: the pin of
+oracle/proj_oracle.c and oracle/impl_oracle.c.  See oracle/refbuild/ts_driver.cc for the modes."""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_ref", "libsarasts_d3.so")
+DIVERGENCE, CORRECTION, IMPOSE_BCS, IMPLICIT, STEP_TAIL = range(5)
+FIELDS = ("vx", "vy", "vz", "P", "Pp", "mgRHS", "rhs_x", "rhs_y", "rhs_z")
+
+
+class TsParams(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("xInd", "yInd", "zInd", "npX", "npY", "xPer", "yPer", "zPer", "xGrid", "yGrid", "zGrid")] + \
+               [(k, C.c_double) for k in ("betaX", "betaY", "betaZ", "Lx", "Ly", "Lz")] + \
+               [(k, C.c_int) for k in ("vcDepth", "vcCount", "preSmooth", "postSmooth", "gsSmooth", "resType")] + \
+               [("mgTolerance", C.c_double), ("probType", C.c_int), ("Re", C.c_double), ("dt", C.c_double), ("cnTolerance", C.c_double)]
+
+
+class RankFields(C.Structure):
+    _fields_ = [("f", C.POINTER(C.c_double) * 9)]
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(LIB)
+        _lib.sarasts_extents.argtypes = [C.POINTER(TsParams), C.POINTER(C.c_int)]
+        _lib.sarasts_run.argtypes = [C.c_char_p, C.POINTER(TsParams), C.POINTER(RankFields), C.c_int]
+        _lib.sarasts_run.restype = C.c_int
+    return _lib
+
+
+def params(cfg, prob_type=1, Re=1000.0, dt=0.01, cn_tolerance=1e-6):
+    """cfg: an Oracle.cfg dictionary (oracle/mgoracle.py)"""
+    p = TsParams()
+    for k, _ in TsParams._fields_:
+        if k in cfg:
+            setattr(p, k, cfg[k])
+    p.probType, p.Re, p.dt, p.cnTolerance = int(prob_type), float(Re), float(dt), float(cn_tolerance)
+    return p
+
+
+def extents(p):
+    out = (C.c_int * 27)()
+    _load().sarasts_extents(C.byref(p), out)
+    return {name: tuple(out[3 * q:3 * q + 3]) for q, name in enumerate(FIELDS)}
+
+
+def run(p, mode, fields):
+    """fields: list (one entry per rank) of dicts name -> C-contiguous float64 array in the field's padded layout; arrays of
+    vx, vy, vz, P, Pp, mgRHS are overwritten with the reference's results, missing entries keep the constructor's values."""
+    nr = p.npX * p.npY
+    assert len(fields) == nr
+    ext = extents(p)
+    arr = (RankFields * nr)()
+    for r, d in enumerate(fields):
+        for q, name in enumerate(FIELDS):
+            a = d.get(name)
+            if a is None:
+                arr[r].f[q] = None
+                continue
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.shape == ext[name], (name, a.shape, ext[name])
+            arr[r].f[q] = a.ctypes.data_as(C.POINTER(C.c_double))
+    with tempfile.TemporaryDirectory() as wd:
+        rc = _load().sarasts_run(wd.encode(), C.byref(p), arr, int(mode))
+    if rc != 0:
+        raise RuntimeError("sarasts_run failed")

@@ -12,7 +12,11 @@
  *   - the handful of expression forms the sources use (unary minus, array - array,
  *     fabs, pow(array, scalar)) evaluated eagerly into temporaries: the floating-point
  *     operations and their order are the same as lazy evaluation;
- *   - full reductions max / mean / sum in storage order (one sequential accumulator).
+ *   - full reductions max / mean / sum in storage order (one sequential accumulator);
+ *   - (for the reference's lib/field, lib/boundary and src/solvers, which the test infrastructure compiles unmodified to pin its
+ *     CPU restatements of the projection step and the implicit solves) element-wise + - * / between arrays, views and scalars, and the tensor-index form
+ *     `A1(range)(i) * B3` (firstIndex / secondIndex / thirdIndex): all evaluated eagerly into temporaries, which performs the same
+ *     floating-point operations in the same order per element as Blitz's lazy expression templates.
  * With a real Blitz++ installation this directory is simply left off the include path.
  */
 #ifndef SARAS_COMPAT_BLITZ_ARRAY_H
@@ -143,10 +147,22 @@ class RectDomain {
     RectDomain(const TinyVector<int, N> &lb, const TinyVector<int, N> &ub) : lb_(lb), ub_(ub) {}
     const TinyVector<int, N> &lbound() const { return lb_; }
     const TinyVector<int, N> &ubound() const { return ub_; }
+    TinyVector<int, N> &lbound() { return lb_; }
+    TinyVector<int, N> &ubound() { return ub_; }
     int lbound(int d) const { return lb_[d]; }
     int ubound(int d) const { return ub_[d]; }
     Range operator[](int d) const { return Range(lb_[d], ub_[d]); }
 };
+
+/* ------------------------------------------------------------------ tensor-index placeholders */
+struct firstIndex {};
+struct secondIndex {};
+struct thirdIndex {};
+enum { firstDim = 0, secondDim = 1, thirdDim = 2 };
+template <class T, int N> class Array;
+/* `A1(i)`: the value of the 1-D array at the ABSOLUTE index of dimension D of the array it is combined with */
+template <class T, int D>
+struct IndexedVec { Array<T, 1> v; };
 
 /* ------------------------------------------------------------------ Array */
 template <class A> struct is_range_ : std::false_type {};
@@ -267,6 +283,21 @@ class Array {
         return zero_[off];
     }
 
+    /* ---- tensor-index forms ---- */
+    IndexedVec<T, 0> operator()(firstIndex) const { static_assert(N == 1, "rank"); IndexedVec<T, 0> r; r.v.reference(*this); return r; }
+    IndexedVec<T, 1> operator()(secondIndex) const { static_assert(N == 1, "rank"); IndexedVec<T, 1> r; r.v.reference(*this); return r; }
+    IndexedVec<T, 2> operator()(thirdIndex) const { static_assert(N == 1, "rank"); IndexedVec<T, 2> r; r.v.reference(*this); return r; }
+    const Array &operator()(firstIndex, secondIndex, thirdIndex) const { static_assert(N == 3, "rank"); return *this; }
+    /* element-wise combination with a 1-D array indexed along dimension D (absolute indices) */
+    template <int D, class F>
+    Array zipIndexed(const Array<T, 1> &v, F f) const {
+        Array r;
+        int b[N]; for (int d = 0; d < N; d++) b[d] = base_[d];
+        r.setup(ext_, b);
+        forEachIndex([&](const int *p) { r.atPos(p) = f(v(p[D] + base_[D]), atPos(p)); });
+        return r;
+    }
+
     /* ---- subarrays (views) ---- */
    private:
     /* restrict dimension d of *this (in place, as a view) to Range r: the index base is kept */
@@ -379,15 +410,63 @@ class Array {
 };
 
 /* ---- eager expressions ---- */
+template <class S> struct is_scalar_ : std::integral_constant<bool, std::is_arithmetic<S>::value> {};
 template <class T, int N> Array<T, N> operator-(const Array<T, N> &a) { return a.map([](const T &x) { return -x; }); }
-template <class T, int N> Array<T, N> operator-(const Array<T, N> &a, const Array<T, N> &b) { return a.zip(b, [](const T &x, const T &y) { return x - y; }); }
-template <class T, int N> Array<T, N> operator+(const Array<T, N> &a, const Array<T, N> &b) { return a.zip(b, [](const T &x, const T &y) { return x + y; }); }
-template <class T, int N> Array<T, N> operator*(const Array<T, N> &a, const T &s) { return a.map([&](const T &x) { return x * s; }); }
-template <class T, int N> Array<T, N> operator*(const T &s, const Array<T, N> &a) { return a.map([&](const T &x) { return s * x; }); }
-template <class T, int N> Array<T, N> operator/(const Array<T, N> &a, const T &s) { return a.map([&](const T &x) { return x / s; }); }
+#define SARAS_ARR_BINOP(op)                                                                                                   \
+    template <class T, int N>                                                                                                 \
+    Array<T, N> operator op(const Array<T, N> &a, const Array<T, N> &b) { return a.zip(b, [](const T &x, const T &y) { return x op y; }); } \
+    template <class T, int N, class S, typename std::enable_if<is_scalar_<S>::value, int>::type = 0>                           \
+    Array<T, N> operator op(const Array<T, N> &a, const S &s) { const T t = T(s); return a.map([&](const T &x) { return x op t; }); }      \
+    template <class T, int N, class S, typename std::enable_if<is_scalar_<S>::value, int>::type = 0>                           \
+    Array<T, N> operator op(const S &s, const Array<T, N> &a) { const T t = T(s); return a.map([&](const T &x) { return t op x; }); }      \
+    template <class T, int D>                                                                                                  \
+    Array<T, 3> operator op(const IndexedVec<T, D> &v, const Array<T, 3> &a) { return a.template zipIndexed<D>(v.v, [](const T &x, const T &y) { return x op y; }); } \
+    template <class T, int D>                                                                                                  \
+    Array<T, 3> operator op(const Array<T, 3> &a, const IndexedVec<T, D> &v) { return a.template zipIndexed<D>(v.v, [](const T &x, const T &y) { return y op x; }); } \
+    template <class T, int D, class S, typename std::enable_if<is_scalar_<S>::value, int>::type = 0>                           \
+    IndexedVec<T, D> operator op(const S &s, const IndexedVec<T, D> &v) { IndexedVec<T, D> r; const T t = T(s); r.v.reference(v.v.map([&](const T &x) { return t op x; })); return r; } \
+    template <class T, int D, class S, typename std::enable_if<is_scalar_<S>::value, int>::type = 0>                           \
+    IndexedVec<T, D> operator op(const IndexedVec<T, D> &v, const S &s) { IndexedVec<T, D> r; const T t = T(s); r.v.reference(v.v.map([&](const T &x) { return x op t; })); return r; }
+SARAS_ARR_BINOP(+)
+SARAS_ARR_BINOP(-)
+SARAS_ARR_BINOP(*)
+SARAS_ARR_BINOP(/)
+#undef SARAS_ARR_BINOP
 template <class T, int N> Array<T, N> fabs(const Array<T, N> &a) { return a.map([](const T &x) { return T(std::fabs(x)); }); }
 template <class T, int N> Array<T, N> abs(const Array<T, N> &a) { return a.map([](const T &x) { return T(std::fabs(x)); }); }
+template <class T, int N> Array<T, N> sqrt(const Array<T, N> &a) { return a.map([](const T &x) { return T(std::sqrt(x)); }); }
 template <class T, int N, class E> Array<T, N> pow(const Array<T, N> &a, E e) { return a.map([&](const T &x) { return T(std::pow(x, e)); }); }
+template <class T, int N> Array<T, N> pow2(const Array<T, N> &a) { return a.map([](const T &x) { return x * x; }); }
+
+/* Stencil operators (blitz/array/stencil-et.h): present so that the reference's derivative.cc COMPILES; nothing this
+ * repository executes evaluates them (computeDiff / computeNLin are outside the pinned paths).  Same extents as the operand,
+ * difference taken where both neighbours exist, 0 on the rim. */
+template <class T>
+Array<T, 3> central12n(const Array<T, 3> &a, int dim) {
+    Array<T, 3> r = a.copy();
+    r = T(0);
+    TinyVector<int, 3> lb = a.lbound(), ub = a.ubound();
+    for (int i = lb[0]; i <= ub[0]; i++) for (int j = lb[1]; j <= ub[1]; j++) for (int k = lb[2]; k <= ub[2]; k++) {
+        int p[3] = {i, j, k}, m[3] = {i, j, k};
+        p[dim] += 1; m[dim] -= 1;
+        if (m[dim] < lb[dim] || p[dim] > ub[dim]) continue;
+        r(i, j, k) = a(p[0], p[1], p[2]) - a(m[0], m[1], m[2]);
+    }
+    return r;
+}
+template <class T>
+Array<T, 3> central22n(const Array<T, 3> &a, int dim) {
+    Array<T, 3> r = a.copy();
+    r = T(0);
+    TinyVector<int, 3> lb = a.lbound(), ub = a.ubound();
+    for (int i = lb[0]; i <= ub[0]; i++) for (int j = lb[1]; j <= ub[1]; j++) for (int k = lb[2]; k <= ub[2]; k++) {
+        int p[3] = {i, j, k}, m[3] = {i, j, k};
+        p[dim] += 1; m[dim] -= 1;
+        if (m[dim] < lb[dim] || p[dim] > ub[dim]) continue;
+        r(i, j, k) = a(p[0], p[1], p[2]) - T(2) * a(i, j, k) + a(m[0], m[1], m[2]);
+    }
+    return r;
+}
 
 /* ---- full reductions ---- */
 template <class T, int N>

@@ -62,6 +62,9 @@ double MPI_Wtime(void);
 
 int MPI_Type_contiguous(int count, MPI_Datatype oldtype, MPI_Datatype *newtype);
 int MPI_Type_vector(int count, int blocklength, int stride, MPI_Datatype oldtype, MPI_Datatype *newtype);
+#define MPI_ORDER_C 56
+int MPI_Type_create_subarray(int ndims, const int *sizes, const int *subsizes, const int *starts, int order, MPI_Datatype oldtype,
+                             MPI_Datatype *newtype);
 int MPI_Type_commit(MPI_Datatype *type);
 int MPI_Type_free(MPI_Datatype *type);
 

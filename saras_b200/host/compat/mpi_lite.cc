@@ -44,6 +44,7 @@ struct World {
     std::mutex m;
     std::vector<std::unique_ptr<Comm>> comms;
     std::vector<DType> types;
+    std::map<int, std::vector<long>> subarrays;   /* MPI_Type_create_subarray: element offsets of the selected block, C order */
     std::vector<std::vector<Posted>> posted;  /* per world rank */
 } W;
 
@@ -60,6 +61,7 @@ void world_init(int n, bool threaded) {
     W.comms.reserve(1024);
     W.types.clear();
     W.types.reserve(65536);
+    W.subarrays.clear();
     W.posted.assign(n, {});
     auto c = std::make_unique<Comm>();
     for (int r = 0; r < n; r++) c->members.push_back(r);
@@ -94,8 +96,22 @@ int my_rank_in(Comm &c) {
 }
 size_t type_bytes(MPI_Datatype t) { const DType d = type_of(t); return (size_t)d.count * d.blocklen * d.elem; }
 
+static bool subarray_of(MPI_Datatype t, std::vector<long> &off) {
+    std::lock_guard<std::mutex> lk(W.m);
+    auto it = W.subarrays.find((int)t);
+    if (it == W.subarrays.end()) return false;
+    off = it->second;
+    return true;
+}
 void pack(const void *buf, int count, MPI_Datatype t, std::vector<char> &out) {
     const DType d = type_of(t);
+    std::vector<long> off;
+    if (subarray_of(t, off)) {                      /* count must be 1: the only use (mpidata.cc:282-305) */
+        out.resize(off.size() * (size_t)d.elem);
+        for (size_t q = 0; q < off.size(); q++) memcpy(out.data() + q * d.elem, (const char *)buf + (size_t)off[q] * d.elem, (size_t)d.elem);
+        (void)count;
+        return;
+    }
     out.resize((size_t)count * type_bytes(t));
     const char *src = (const char *)buf;
     char *dst = out.data();
@@ -108,6 +124,12 @@ void pack(const void *buf, int count, MPI_Datatype t, std::vector<char> &out) {
 }
 void unpack(void *buf, int count, MPI_Datatype t, const std::vector<char> &in) {
     const DType d = type_of(t);
+    std::vector<long> off;
+    if (subarray_of(t, off)) {
+        for (size_t q = 0; q < off.size(); q++) memcpy((char *)buf + (size_t)off[q] * d.elem, in.data() + q * d.elem, (size_t)d.elem);
+        (void)count;
+        return;
+    }
     char *dst = (char *)buf;
     const char *src = in.data();
     const size_t extent = ((size_t)(d.count - 1) * d.stride + d.blocklen) * d.elem;
@@ -230,6 +252,23 @@ int MPI_Type_vector(int count, int blocklength, int stride, MPI_Datatype oldtype
     const DType o = W.types[(size_t)oldtype];
     W.types.push_back({count, blocklength * o.blocklen, stride * o.blocklen, o.elem});
     *newtype = (int)W.types.size() - 1;
+    return MPI_SUCCESS;
+}
+int MPI_Type_create_subarray(int ndims, const int *sizes, const int *subsizes, const int *starts, int order, MPI_Datatype oldtype,
+                             MPI_Datatype *newtype) {
+    ensure_init();
+    if (order != MPI_ORDER_C || ndims < 1 || ndims > 3) { fprintf(stderr, "mpi-lite: MPI_Type_create_subarray: C order, 1-3 dimensions only\n"); abort(); }
+    std::lock_guard<std::mutex> lk(W.m);
+    const DType o = W.types[(size_t)oldtype];
+    int sz[3] = {1, 1, 1}, sub[3] = {1, 1, 1}, st[3] = {0, 0, 0};
+    for (int d = 0; d < ndims; d++) { sz[3 - ndims + d] = sizes[d]; sub[3 - ndims + d] = subsizes[d]; st[3 - ndims + d] = starts[d]; }
+    std::vector<long> off;
+    off.reserve((size_t)sub[0] * sub[1] * sub[2]);
+    for (int a = 0; a < sub[0]; a++) for (int b = 0; b < sub[1]; b++) for (int c = 0; c < sub[2]; c++)
+        off.push_back(((long)(st[0] + a) * sz[1] + (st[1] + b)) * sz[2] + (st[2] + c));
+    W.types.push_back({(int)off.size(), 1, 1, o.elem * o.count * o.blocklen});
+    *newtype = (int)W.types.size() - 1;
+    W.subarrays[*newtype] = off;
     return MPI_SUCCESS;
 }
 int MPI_Type_commit(MPI_Datatype *) { return MPI_SUCCESS; }

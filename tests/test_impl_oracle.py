@@ -4,8 +4,8 @@
   object (oracle/_ref, grid.cc compiled unmodified);
 * the Jacobi solve is checked through what it must deliver whatever the iteration details: the converged field satisfies
   (1 - dt/(2 Re) Lap) V = rhs in the bulk to cnTolerance (independent numpy statement of hydro_d3.cc:396-402), and the
-  boundary objects leave the values lib/boundary/*.cc prescribe.  The loops themselves are NOT pinned against an execution
-  of the reference (its field / boundary / solver classes cannot be compiled here) -- impl_oracle.c says so in its header."""
+  boundary objects leave the values lib/boundary/*.cc prescribe.  The pin against an EXECUTION of the reference's own
+  hydro_d3::solveVx / Vy / Vz is tests/test_oracle_vs_timestepper.py."""
 import os
 
 import numpy as np

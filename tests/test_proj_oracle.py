@@ -4,8 +4,8 @@
   object (oracle/_ref, compiled unmodified) on uniform and tanh-stretched grids, 1 / 2 / 4 ranks;
 * its divergence / syncData / correction loops are checked against an independent vectorised numpy statement of the Blitz
   expressions (vfield.cc:310-319, plainsf.h:92-98, sfield.cc:197-201, mpidata.cc:105-259).  The reference's lib/field cannot
-  be compiled here (Blitz tensor-index expressions), so these three are NOT pinned against an execution of the reference --
-  oracle/proj_oracle.c says so in its header."""
+  (vfield.cc:310-319, plainsf.h:92-98, sfield.cc:197-201, mpidata.cc:105-259) and the global periodic wrap.  The pin against an
+  EXECUTION of the reference's own field library is tests/test_oracle_vs_timestepper.py."""
 import os
 
 import numpy as np
