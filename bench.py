@@ -496,7 +496,29 @@ def run_b200(a):
         s.synchronize(); barrier()
         lups = sum(lups_per_solve(level_points, pre, post, o["coarse_iters"]) for o in outs_p) / steps
         pts = level_points_local[0]
-        return dict(ms_per_step=ms, value=lups / (ms * 1e-3) / 1e9, unit=UNIT, cycles_per_step=[int(o["cycles"]) for o in outs_p],
+        # implicit solve of Vx (hydro_d3::solveVx with the lid-driven-cavity boundary objects), one rank: Jacobi sweeps
+        # of 40 B per point (update 24, max-norm of the implicit equation 16) plus the boundary planes, one scalar read back per sweep
+        implicit = None
+        if world == 1:
+            try:
+                bt, bv = capi.velocity_bcs(0, 0, 0, 1)
+                idt, iRe = 1.0e-5, 1000.0           # dt / (2 Re h^2) = 5e-3 at h = 2^-10: converges in a few sweeps
+                s.impl_setup(idt, iRe, 1.0e-6, spacing, [np.full(n0[d] + 1, 1.0 / (L * L)) for d in range(3)],
+                             [np.full(n0[d] + 2, 1.0 / (L * L)) for d in range(3)], bt, bv, 1000)
+                cnt = int(np.prod(shapes[capi.PROJ_VX]))
+                s.impl_upload_rhs(0, src[:cnt].reshape(shapes[capi.PROJ_VX]))
+                s.synchronize()
+                s.event_record(2)
+                sweeps, err = s.impl_solve(0)
+                s.event_record(3)
+                ms_i = s.event_elapsed_ms(2, 3)
+                implicit = dict(component="Vx", sweeps=int(sweeps), max_error=float(err), ms=ms_i, ms_per_sweep=ms_i / sweeps,
+                                gbs=40.0 * cnt / (ms_i / sweeps * 1e-3) / 1e9, dt=idt, Re=iRe, cn_tolerance=1.0e-6,
+                                bytes_per_point="40 per sweep: Jacobi update 24 (read V, rhs, write guess) + residual max-norm 16",
+                                api="sarasmg_impl_solve (hydro_d3.cc:370-423 + hydro.cc:386-401)")
+            except Exception as e:
+                implicit = dict(error=str(e)[:300])
+        return dict(implicit_solve=implicit, ms_per_step=ms, value=lups / (ms * 1e-3) / 1e9, unit=UNIT, cycles_per_step=[int(o["cycles"]) for o in outs_p],
                     divergence_ms=ms_div, correction_ms=ms_cor,
                     divergence_gbs=32.0 * pts / (ms_div * 1e-3) / 1e9, correction_gbs=80.0 * pts / (ms_cor * 1e-3) / 1e9,
                     bytes_per_point="divergence 32 (read Vx, Vy, Vz, write mgRHS); correction 80 (copy Pp 16, P += Pp 24, three velocity updates 48 - 8 shared Pp read)",

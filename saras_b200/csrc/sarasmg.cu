@@ -2165,21 +2165,26 @@ int sarasmg_impl_setup(sarasmg_handle s, const sarasmg_impl_desc *d) {
         if (!s->d_impl_met[q]) CU(cudaMalloc(&s->d_impl_met[q], sizeof(double) * len[q]));
         CU(cudaMemcpyAsync(s->d_impl_met[q], src[q], sizeof(double) * len[q], cudaMemcpyHostToDevice, s->st));
     }
-    for (int c = 0; c < 3; c++) {
-        if (!s->d_nse[c]) CU(cudaMalloc(&s->d_nse[c], sizeof(double) * s->vel_elems[c]));
-        if (!s->d_guess[c]) CU(cudaMalloc(&s->d_guess[c], sizeof(double) * s->vel_elems[c]));
-        CU(cudaMemsetAsync(s->d_nse[c], 0, sizeof(double) * s->vel_elems[c], s->st));
-    }
+    /* nseRHS / guessedVelocity of a component are allocated when the component is first used (impl_component) */
     CU(cudaStreamSynchronize(s->st));
     s->impl = *d;
     s->impl.xix2_colloc = s->impl.ety2_colloc = s->impl.ztz2_colloc = s->impl.xix2_staggr = s->impl.ety2_staggr = s->impl.ztz2_staggr = nullptr;
     s->impl_ok = true;
     return 0;
 }
+static int impl_component(S *s, int comp) {
+    if (!s->d_nse[comp]) {
+        CU(cudaMalloc(&s->d_nse[comp], sizeof(double) * s->vel_elems[comp]));
+        CU(cudaMemsetAsync(s->d_nse[comp], 0, sizeof(double) * s->vel_elems[comp], s->st));
+    }
+    if (!s->d_guess[comp]) CU(cudaMalloc(&s->d_guess[comp], sizeof(double) * s->vel_elems[comp]));
+    return 0;
+}
 int sarasmg_impl_upload_rhs(sarasmg_handle s, int comp, const double *host) {
     if (!s || !host || comp < 0 || comp > 2) return set_err("sarasmg_impl_upload_rhs: bad argument");
     if (!s->impl_ok) return set_err("sarasmg_impl_upload_rhs: call sarasmg_impl_setup first");
     CU(cudaSetDevice(s->d.device));
+    TRY(impl_component(s, comp));
     CU(cudaMemcpyAsync(s->d_nse[comp], host, sizeof(double) * s->vel_elems[comp], cudaMemcpyHostToDevice, s->st));
     CU(cudaStreamSynchronize(s->st));
     return 0;
@@ -2223,6 +2228,7 @@ int sarasmg_impl_solve(sarasmg_handle s, int comp, int *sweeps, double *max_erro
     if (!s || comp < 0 || comp > 2) return set_err("sarasmg_impl_solve: bad argument");
     if (!s->impl_ok) return set_err("sarasmg_impl_solve: call sarasmg_impl_setup first");
     CU(cudaSetDevice(s->d.device));
+    TRY(impl_component(s, comp));
     const ImplGeom g = impl_geom(s, comp);
     const ImplCoef c = impl_coef(s);
     const dim3 gs(cdiv(g.ext[2], 256), g.ext[1], g.ext[0]);
