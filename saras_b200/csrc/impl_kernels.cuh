@@ -18,7 +18,16 @@ struct ImplGeom {
     int cs[3], ext[3], lb[3], ub[3], stag[3];       /* core size, padded extent, bulk bounds (field.cc:180-226), staggered? */
     const double *mx, *my, *mz;                     /* xi_x^2, et_y^2, zt_z^2 at this component's points, [i] = index i */
 };
-struct ImplCoef { double hy2hz2, hz2hx2, hx2hy2, hx2hy2hz2, hx, hy, hz, dt, Re, inverseRe; };
+struct ImplCoef {
+    double hy2hz2, hz2hx2, hx2hy2, hx2hy2hz2, hx, hy, hz, dt, Re, inverseRe;
+    /* the loop-invariant divisors of the two point formulas and their reciprocals: x / d is rebuilt exactly from 1/d
+     * (div_inv, or one multiply when d is a power of two), as in the multigrid kernels */
+    double den1, rden1;         /* hx2hy2hz2 * 2.0 * Re */
+    double den2, rden2;         /* Re * hx2hy2hz2 */
+    double hxx, rhxx, hyy, rhyy, hzz, rhzz;     /* hx*hx, hy*hy, hz*hz */
+    int p2;                     /* hx*hx, hy*hy, hz*hz are powers of two (every SARAS grid: 2^n intervals) */
+};
+__device__ __forceinline__ double impl_div(const double a, const double d, const double r, const int p2) { return p2 ? a * r : div_inv(a, d, r); }
 
 __device__ __forceinline__ long long impl_at(const ImplGeom &g, int i, int j, int k) {
     return ((long long)(i + 1) * g.ext[1] + (j + 1)) * g.ext[2] + (k + 1);
@@ -28,19 +37,20 @@ __device__ __forceinline__ long long impl_at(const ImplGeom &g, int i, int j, in
  * reference's guessedVelocity is never written outside the bulk and `V.Vx.F = guessedVelocity.Vx` copies all of it) */
 __global__ void __launch_bounds__(256) k_impl_sweep(const double *__restrict__ V, const double *__restrict__ rhs, double *__restrict__ G,
                                                     const ImplGeom g, const ImplCoef c) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x - 1;
-    const int j = (int)blockIdx.y - 1, i = (int)blockIdx.z - 1;
-    if (k > g.ext[2] - 2) return;
+    /* one x-plane per blockIdx.y, its (j, k) rows flattened over blockIdx.x: no idle tail threads when ext[2] = 2^m + 3 */
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= g.ext[1] * g.ext[2]) return;
+    const int i = (int)blockIdx.y - 1, j = q / g.ext[2] - 1, k = q - (j + 1) * g.ext[2] - 1;
     const long long o = impl_at(g, i, j, k);
     double r = 0.0;
     if (i >= g.lb[0] && i <= g.ub[0] && j >= g.lb[1] && j <= g.ub[1] && k >= g.lb[2] && k <= g.ub[2]) {
         const long long sx = (long long)g.ext[1] * g.ext[2], sy = g.ext[2];
         const double mx = g.mx[i], my = g.my[j], mz = g.mz[k];
-        r = ((c.hy2hz2 * mx * (V[o + sx] + V[o - sx]) +
-              c.hz2hx2 * my * (V[o + sy] + V[o - sy]) +
-              c.hx2hy2 * mz * (V[o + 1] + V[o - 1])) *
-             c.dt / (c.hx2hy2hz2 * 2.0 * c.Re) + rhs[o]) /
-            (1.0 + c.dt * ((c.hy2hz2 * mx + c.hz2hx2 * my + c.hx2hy2 * mz)) / (c.Re * c.hx2hy2hz2));
+        r = (div_inv((c.hy2hz2 * mx * (V[o + sx] + V[o - sx]) +
+                      c.hz2hx2 * my * (V[o + sy] + V[o - sy]) +
+                      c.hx2hy2 * mz * (V[o + 1] + V[o - 1])) *
+                     c.dt, c.den1, c.rden1) + rhs[o]) /
+            (1.0 + div_inv(c.dt * ((c.hy2hz2 * mx + c.hz2hx2 * my + c.hx2hy2 * mz)), c.den2, c.rden2));
     }
     G[o] = r;
 }
@@ -49,21 +59,22 @@ __global__ void __launch_bounds__(256) k_impl_sweep(const double *__restrict__ V
 __global__ void __launch_bounds__(256) k_impl_error(const double *__restrict__ V, const double *__restrict__ rhs, const ImplGeom g, const ImplCoef c,
                                                     double *__restrict__ part) {
     __shared__ double sm[32];
-    const int k = blockIdx.x * blockDim.x + threadIdx.x + g.lb[2];
-    const int j = (int)blockIdx.y + g.lb[1], i = (int)blockIdx.z + g.lb[0];
+    const int bk = g.ub[2] - g.lb[2] + 1, bj = g.ub[1] - g.lb[1] + 1;     /* bulk rows of one x-plane, flattened */
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)blockIdx.y + g.lb[0], j = q / bk + g.lb[1], k = q - (q / bk) * bk + g.lb[2];
     double e = 0.0;
-    if (k <= g.ub[2]) {
+    if (q < bj * bk) {
         const long long o = impl_at(g, i, j, k);
         const long long sx = (long long)g.ext[1] * g.ext[2], sy = g.ext[2];
         const double v = V[o];
-        const double lap = v - (g.mx[i] * (V[o + sx] - 2.0 * v + V[o - sx]) / (c.hx * c.hx) +
-                                g.my[j] * (V[o + sy] - 2.0 * v + V[o - sy]) / (c.hy * c.hy) +
-                                g.mz[k] * (V[o + 1] - 2.0 * v + V[o - 1]) / (c.hz * c.hz)) *
+        const double lap = v - (impl_div(g.mx[i] * (V[o + sx] - 2.0 * v + V[o - sx]), c.hxx, c.rhxx, c.p2) +
+                                impl_div(g.my[j] * (V[o + sy] - 2.0 * v + V[o - sy]), c.hyy, c.rhyy, c.p2) +
+                                impl_div(g.mz[k] * (V[o + 1] - 2.0 * v + V[o - 1]), c.hzz, c.rhzz, c.p2)) *
                                    0.5 * c.dt * c.inverseRe;
         e = fabs(lap - rhs[o]);
     }
     e = block_reduce<true>(e, sm);
-    if (threadIdx.x == 0) part[blockIdx.x + gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z)] = e;
+    if (threadIdx.x == 0) part[blockIdx.x + (long long)gridDim.x * blockIdx.y] = e;
 }
 
 /* syncData of one rank (mpidata.cc:278-306): periodic self faces over the core rows, then the four edge columns (always) */

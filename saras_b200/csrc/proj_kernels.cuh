@@ -36,9 +36,11 @@ __device__ __forceinline__ double pdiv(const double a, const double d, const dou
  * (vfield.cc:310-319, hydro_d3.cc:327).  out = the solver's rhs input buffer (pitched level-0 layout), written over its whole padded box */
 __global__ void __launch_bounds__(128) k_proj_divergence(const double *__restrict__ vx, const double *__restrict__ vy, const double *__restrict__ vz,
                                                          double *__restrict__ out, const LevelView L, const ProjView V, const double inv_dt) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x - 1;
-    const int j = (int)blockIdx.y - 1, i = (int)blockIdx.z - 1;
-    if (k > V.nz) return;
+    /* one x-plane per blockIdx.y, its padded (j, k) rows flattened over blockIdx.x (no idle tail threads per row) */
+    const int Fz = V.nz + 2;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (V.ny + 2) * Fz) return;
+    const int i = (int)blockIdx.y - 1, j = q / Fz - 1, k = q - (j + 1) * Fz - 1;
     double r = 0.0;
     if (i >= 0 && i < V.nx && j >= 0 && j < V.ny && k >= 0 && k < V.nz) {
         const double a = pdiv(V.xs[i] * (vx[pvx(V, i, j, k)] - vx[pvx(V, i - 1, j, k)]), V.dXi, V.rXi, V.p2);
@@ -86,9 +88,10 @@ __global__ void __launch_bounds__(256) k_proj_sync_edges(double *__restrict__ A,
 __global__ void __launch_bounds__(128) k_proj_correct(const double *__restrict__ pp, double *__restrict__ P, double *__restrict__ vx,
                                                       double *__restrict__ vy, double *__restrict__ vz, const LevelView L, const ProjView V,
                                                       const double dt) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x - 1;
-    const int j = (int)blockIdx.y - 1, i = (int)blockIdx.z - 1;
-    if (k > V.nz) return;
+    const int Fz = V.nz + 2;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (V.ny + 2) * Fz) return;
+    const int i = (int)blockIdx.y - 1, j = q / Fz - 1, k = q - (j + 1) * Fz - 1;
     const long long o = mg_at(L, i, j, k);
     const double p0 = pp[o];
     P[o] = P[o] + p0;

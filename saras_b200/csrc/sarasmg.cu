@@ -2051,7 +2051,7 @@ int sarasmg_proj_download(sarasmg_handle s, int which, double *host) {
 
 static int proj_divergence(S *s, double inv_dt) {
     const LevelView &v0 = s->lev[0].v;
-    const dim3 grid(cdiv(v0.Fz, 128), v0.Fy, v0.Fx);
+    const dim3 grid(cdiv((long long)v0.Fy * v0.Fz, 128), v0.Fx, 1);
     k_proj_divergence<<<grid, 128, 0, s->st>>>(s->d_vel[0], s->d_vel[1], s->d_vel[2], s->d_in_rhs, v0, s->pv, inv_dt);
     return kcheck(s, "k_proj_divergence");
 }
@@ -2098,7 +2098,7 @@ static int proj_correct(S *s, double dt) {
         k_proj_sync_unpack<<<nb, 256, 0, s->st>>>(s->d_in_p, v0, s->psync, s->d_psync[1]);
         TRY(kcheck(s, "k_proj_sync_unpack"));
     }
-    const dim3 grid(cdiv(v0.Fz, 128), v0.Fy, v0.Fx);
+    const dim3 grid(cdiv((long long)v0.Fy * v0.Fz, 128), v0.Fx, 1);
     k_proj_correct<<<grid, 128, 0, s->st>>>(s->d_in_p, s->d_presP, s->d_vel[0], s->d_vel[1], s->d_vel[2], v0, s->pv, dt);
     return kcheck(s, "k_proj_correct");
 }
@@ -2148,6 +2148,11 @@ static ImplCoef impl_coef(const S *s) {
     ImplCoef c;
     c.hy2hz2 = d.hy2hz2; c.hz2hx2 = d.hz2hx2; c.hx2hy2 = d.hx2hy2; c.hx2hy2hz2 = d.hx2hy2hz2;
     c.hx = d.hx; c.hy = d.hy; c.hz = d.hz; c.dt = d.dt; c.Re = d.Re; c.inverseRe = 1.0 / d.Re;     /* hydro.cc:65 */
+    c.den1 = d.hx2hy2hz2 * 2.0 * d.Re; c.rden1 = 1.0 / c.den1;
+    c.den2 = d.Re * d.hx2hy2hz2; c.rden2 = 1.0 / c.den2;
+    c.hxx = d.hx * d.hx; c.hyy = d.hy * d.hy; c.hzz = d.hz * d.hz;
+    c.rhxx = 1.0 / c.hxx; c.rhyy = 1.0 / c.hyy; c.rhzz = 1.0 / c.hzz;
+    c.p2 = (is_pow2(c.hxx) && is_pow2(c.hyy) && is_pow2(c.hzz) && !s->no_pow2) ? 1 : 0;
     return c;
 }
 int sarasmg_impl_setup(sarasmg_handle s, const sarasmg_impl_desc *d) {
@@ -2231,10 +2236,10 @@ int sarasmg_impl_solve(sarasmg_handle s, int comp, int *sweeps, double *max_erro
     TRY(impl_component(s, comp));
     const ImplGeom g = impl_geom(s, comp);
     const ImplCoef c = impl_coef(s);
-    const dim3 gs(cdiv(g.ext[2], 256), g.ext[1], g.ext[0]);
+    const dim3 gs(cdiv((long long)g.ext[1] * g.ext[2], 256), g.ext[0], 1);
     const int bn[3] = {g.ub[0] - g.lb[0] + 1, g.ub[1] - g.lb[1] + 1, g.ub[2] - g.lb[2] + 1};
     if (bn[0] < 1 || bn[1] < 1 || bn[2] < 1) return set_err("sarasmg_impl_solve: empty bulk");
-    const dim3 ge(cdiv(bn[2], 256), bn[1], bn[0]);
+    const dim3 ge(cdiv((long long)bn[1] * bn[2], 256), bn[0], 1);
     const size_t nb = (size_t)ge.x * ge.y * ge.z;
     TRY(ensure_part(s, nb + 16));
     long long iterCount = 0;

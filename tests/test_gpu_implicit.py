@@ -48,7 +48,10 @@ def test_velocity_bcs_bitexact(case):
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
-def test_implicit_solves_bitexact(case):
+@pytest.mark.parametrize("general", [0, 1], ids=["pow2", "general_div"])
+def test_implicit_solves_bitexact(case, general, monkeypatch):
+    if general:         # the divisors hx*hx .. are powers of two on every SARAS grid; force the exact-reciprocal sequence instead
+        monkeypatch.setenv("SARASMG_NO_POW2", "1")
     o, s, io = _setup(case)
     sh = mo.proj_shapes(io.n)
     rng = np.random.default_rng(22)
