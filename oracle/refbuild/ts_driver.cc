@@ -16,6 +16,8 @@
  *   mode 2  imposeUBCs(); imposeVBCs(); imposeWBCs();                                                   :364-366
  *   mode 3  solveVx(); solveVy(); solveVz();                                                            :306-316
  *   mode 4  modes 3, 0, mgSolve, 1, 2 in sequence: the tail of timeAdvance from nseRHS on               :303-366
+ *   mode 6  nseRHS = 0; V.computeDiff(nseRHS);  (returned in the nseRHS slots)                          :259-265
+ *   mode 7  nSteps x timeAdvance() from the configured initial condition (inputs given replace it)      :254-367
  * Fields go in and out as the padded Blitz arrays of every rank.  Ranks are threads (mpi-lite).
  */
 #include <cstdio>
@@ -53,6 +55,9 @@ typedef struct {
     double mgTolerance;
     int probType;           /* "Problem Type": 1 lid-driven cavity, 3 inflow / outflow, 4 channel, ... (hydro.cc:287-371) */
     double Re, dt, cnTolerance;
+    int icType;             /* "Initial Condition": 0 zero, 1 Taylor-Green vortex, 2 / 3 channel profiles (hydro_d3.cc:88-101) */
+    int nSteps;             /* mode 7: number of timeAdvance() calls */
+    int outputOnly;         /* bit q set: field q of ts_rank_fields is only written (the constructor's / initial condition's value is kept as input) */
 } ts_params;
 
 /* per rank: Vx, Vy, Vz, P, Pp, mgRHS, nseRHS.Vx, nseRHS.Vy, nseRHS.Vz (any may be NULL: left as the constructor set it) */
@@ -72,7 +77,7 @@ void write_yaml(const ts_params &p, const std::string &dir) {
     char mesh[4] = {p.xGrid == 2 ? 'D' : 'U', p.yGrid == 2 ? 'D' : 'U', p.zGrid == 2 ? 'D' : 'U', 0};
     f.precision(17);
     f << "\"Program\":\n"
-      << "    \"Problem Type\": " << p.probType << "\n    \"Initial Condition\": 0\n    \"Domain Type\": \"" << dom << "\"\n    \"RBC Type\": 1\n"
+      << "    \"Problem Type\": " << p.probType << "\n    \"Initial Condition\": " << p.icType << "\n    \"Domain Type\": \"" << dom << "\"\n    \"RBC Type\": 1\n"
       << "    \"Reynolds Number\": " << p.Re << "\n    \"Rossby Number\": 12\n    \"Rayleigh Number\": 10000\n    \"Prandtl Number\": 0.71\n"
       << "    \"Taylor Number\": 0.0\n    \"X Length\": " << p.Lx << "\n    \"Y Length\": " << p.Ly << "\n    \"Z Length\": " << p.Lz << "\n"
       << "    \"Heating Plate\": false\n    \"Plate Radius\": 0.25\n    \"Force\": 0\n"
@@ -100,10 +105,11 @@ void rank_main(void *arg) {
     hydro_d3 H(gridData, inputParams, mpi);      /* P = 1, zero initial condition, checkPeriodic, initVBC, imposeU/V/WBCs */
     H.dt = p.dt;                                 /* hydro_d3::solvePDE sets dt = inputParams.tStp (hydro_d3.cc:157); set here as no solvePDE runs */
     ts_rank_fields &F = job->flds[mpi.rank];
-    put(H.V.Vx.F, F.f[0]); put(H.V.Vy.F, F.f[1]); put(H.V.Vz.F, F.f[2]);
-    put(H.P.F.F, F.f[3]); put(H.Pp.F, F.f[4]); put(H.mgRHS.F, F.f[5]);
-    put(H.nseRHS.Vx, F.f[6]); put(H.nseRHS.Vy, F.f[7]); put(H.nseRHS.Vz, F.f[8]);
+    blitz::Array<real, 3> *dst[9] = {&H.V.Vx.F, &H.V.Vy.F, &H.V.Vz.F, &H.P.F.F, &H.Pp.F, &H.mgRHS.F, &H.nseRHS.Vx, &H.nseRHS.Vy, &H.nseRHS.Vz};
+    for (int q = 0; q < 9; q++) if (!((p.outputOnly >> q) & 1)) put(*dst[q], F.f[q]);
     const int m = job->mode;
+    if (m == 6) { H.nseRHS = 0.0; H.V.computeDiff(H.nseRHS); }
+    if (m == 7) for (int n = 0; n < p.nSteps; n++) H.timeAdvance();
     if (m == 3 || m == 4) { H.solveVx(); H.solveVy(); H.solveVz(); }
     if (m == 0 || m == 4) { H.V.divergence(H.mgRHS, H.P); H.mgRHS *= 1.0 / H.dt; }
     if (m == 4 || m == 5) H.mgSolver.mgSolve(H.Pp, H.mgRHS);      /* mode 5: mgSolve alone (debugging aid) */
@@ -117,6 +123,7 @@ void rank_main(void *arg) {
     if (m == 2 || m == 4) { H.imposeUBCs(); H.imposeVBCs(); H.imposeWBCs(); }
     get(H.V.Vx.F, F.f[0]); get(H.V.Vy.F, F.f[1]); get(H.V.Vz.F, F.f[2]);
     get(H.P.F.F, F.f[3]); get(H.Pp.F, F.f[4]); get(H.mgRHS.F, F.f[5]);
+    get(H.nseRHS.Vx, F.f[6]); get(H.nseRHS.Vy, F.f[7]); get(H.nseRHS.Vz, F.f[8]);
 }
 
 }  // namespace

@@ -9,7 +9,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "libsarasts_d3.so")
-DIVERGENCE, CORRECTION, IMPOSE_BCS, IMPLICIT, STEP_TAIL = range(5)
+DIVERGENCE, CORRECTION, IMPOSE_BCS, IMPLICIT, STEP_TAIL, MGSOLVE, COMPUTE_DIFF, TIME_ADVANCE = range(8)
 FIELDS = ("vx", "vy", "vz", "P", "Pp", "mgRHS", "rhs_x", "rhs_y", "rhs_z")
 
 
@@ -17,7 +17,8 @@ class TsParams(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("xInd", "yInd", "zInd", "npX", "npY", "xPer", "yPer", "zPer", "xGrid", "yGrid", "zGrid")] + \
                [(k, C.c_double) for k in ("betaX", "betaY", "betaZ", "Lx", "Ly", "Lz")] + \
                [(k, C.c_int) for k in ("vcDepth", "vcCount", "preSmooth", "postSmooth", "gsSmooth", "resType")] + \
-               [("mgTolerance", C.c_double), ("probType", C.c_int), ("Re", C.c_double), ("dt", C.c_double), ("cnTolerance", C.c_double)]
+               [("mgTolerance", C.c_double), ("probType", C.c_int), ("Re", C.c_double), ("dt", C.c_double), ("cnTolerance", C.c_double),
+                ("icType", C.c_int), ("nSteps", C.c_int), ("outputOnly", C.c_int)]
 
 
 class RankFields(C.Structure):
@@ -41,13 +42,15 @@ def _load():
     return _lib
 
 
-def params(cfg, prob_type=1, Re=1000.0, dt=0.01, cn_tolerance=1e-6):
+def params(cfg, prob_type=1, Re=1000.0, dt=0.01, cn_tolerance=1e-6, ic_type=0, n_steps=1, output_only=()):
     """cfg: an Oracle.cfg dictionary (oracle/mgoracle.py)"""
     p = TsParams()
     for k, _ in TsParams._fields_:
         if k in cfg:
             setattr(p, k, cfg[k])
     p.probType, p.Re, p.dt, p.cnTolerance = int(prob_type), float(Re), float(dt), float(cn_tolerance)
+    p.icType, p.nSteps = int(ic_type), int(n_steps)
+    p.outputOnly = sum(1 << FIELDS.index(name) for name in output_only)      # these fields keep the reference's own initial values
     return p
 
 
@@ -59,7 +62,7 @@ def extents(p):
 
 def run(p, mode, fields):
     """fields: list (one entry per rank) of dicts name -> C-contiguous float64 array in the field's padded layout; arrays of
-    vx, vy, vz, P, Pp, mgRHS are overwritten with the reference's results, missing entries keep the constructor's values."""
+    are overwritten with the reference's results (all nine, when given); missing entries keep the constructor's values."""
     nr = p.npX * p.npY
     assert len(fields) == nr
     ext = extents(p)

@@ -438,35 +438,32 @@ template <class T, int N> Array<T, N> sqrt(const Array<T, N> &a) { return a.map(
 template <class T, int N, class E> Array<T, N> pow(const Array<T, N> &a, E e) { return a.map([&](const T &x) { return T(std::pow(x, e)); }); }
 template <class T, int N> Array<T, N> pow2(const Array<T, N> &a) { return a.map([](const T &x) { return x * x; }); }
 
-/* Stencil operators (blitz/array/stencil-et.h): present so that the reference's derivative.cc COMPILES; nothing this
- * repository executes evaluates them (computeDiff / computeNLin are outside the pinned paths).  Same extents as the operand,
- * difference taken where both neighbours exist, 0 on the rim. */
-template <class T>
-Array<T, 3> central12n(const Array<T, 3> &a, int dim) {
-    Array<T, 3> r = a.copy();
-    r = T(0);
-    TinyVector<int, 3> lb = a.lbound(), ub = a.ubound();
-    for (int i = lb[0]; i <= ub[0]; i++) for (int j = lb[1]; j <= ub[1]; j++) for (int k = lb[2]; k <= ub[2]; k++) {
+/* Stencil operators (blitz/array/stencil-et.h) as the reference's derivative.cc uses them:
+ *     out(Range(0, core_ub), all, all) = central12n(F, 0);
+ * i.e. the stencil expression's domain is the operand's domain shrunk by one point at each end of `dim` -- where both
+ * neighbours exist -- and it is assigned, position by position, to a destination view of exactly that shape.  Returned here as
+ * a compact array of the shrunk shape whose element p along `dim` is the stencil applied at operand index lbound + 1 + p
+ * (central12n: A(+1) - A(-1); central22n: A(+1) - 2 A + A(-1), in that order).  Not on any path this repository pins bit for
+ * bit (computeDiff / computeNLin); tests/test_reference_timestep.py checks them against analytic derivatives. */
+template <class T, class F>
+Array<T, 3> stencil3_(const Array<T, 3> &a, int dim, F f) {
+    TinyVector<int, 3> lb = a.lbound(), ext = a.extent();
+    ext[dim] -= 2;
+    Array<T, 3> r(ext);
+    TinyVector<int, 3> nb = lb;
+    nb[dim] += 1;
+    r.reindexSelf(nb);
+    for (int i = nb[0]; i < nb[0] + ext[0]; i++) for (int j = nb[1]; j < nb[1] + ext[1]; j++) for (int k = nb[2]; k < nb[2] + ext[2]; k++) {
         int p[3] = {i, j, k}, m[3] = {i, j, k};
         p[dim] += 1; m[dim] -= 1;
-        if (m[dim] < lb[dim] || p[dim] > ub[dim]) continue;
-        r(i, j, k) = a(p[0], p[1], p[2]) - a(m[0], m[1], m[2]);
+        r(i, j, k) = f(a(p[0], p[1], p[2]), a(i, j, k), a(m[0], m[1], m[2]));
     }
     return r;
 }
 template <class T>
-Array<T, 3> central22n(const Array<T, 3> &a, int dim) {
-    Array<T, 3> r = a.copy();
-    r = T(0);
-    TinyVector<int, 3> lb = a.lbound(), ub = a.ubound();
-    for (int i = lb[0]; i <= ub[0]; i++) for (int j = lb[1]; j <= ub[1]; j++) for (int k = lb[2]; k <= ub[2]; k++) {
-        int p[3] = {i, j, k}, m[3] = {i, j, k};
-        p[dim] += 1; m[dim] -= 1;
-        if (m[dim] < lb[dim] || p[dim] > ub[dim]) continue;
-        r(i, j, k) = a(p[0], p[1], p[2]) - T(2) * a(i, j, k) + a(m[0], m[1], m[2]);
-    }
-    return r;
-}
+Array<T, 3> central12n(const Array<T, 3> &a, int dim) { return stencil3_(a, dim, [](const T &p, const T &, const T &m) { return p - m; }); }
+template <class T>
+Array<T, 3> central22n(const Array<T, 3> &a, int dim) { return stencil3_(a, dim, [](const T &p, const T &c, const T &m) { return p - T(2) * c + m; }); }
 
 /* ---- full reductions ---- */
 template <class T, int N>

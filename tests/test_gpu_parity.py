@@ -413,3 +413,35 @@ def test_fused_residual_restriction_equals_two_passes(case, monkeypatch):
         s.close()
     assert np.array_equal(outs[0], outs[1])
     assert launches[0] != launches[1], launches
+
+
+def test_mg_solve_on_captured_time_step_rhs():
+    """BASELINE config C3's problem with REAL right-hand sides: tests/golden/tgv_step_33.npz holds mgRHS = div(V*) / dt of two
+    consecutive hydro_d3::timeAdvance() calls of the Taylor-Green vortex (Re 1600, periodic 2 pi box, Gauss-Seidel multigrid) as the
+    reference's own time stepper formed them, and the Pp it was left with (tests/golden/make_golden_timestep.py;
+    tests/test_reference_timestep.py pins the oracle on them).  Same bar as test_mg_solve_parity, Pp of step 1 being the initial
+    guess of step 2 as in the time stepper."""
+    import os
+    from tests.golden import make_golden_timestep as gt
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tgv_step_33.npz"))
+    o, s = _mk(dict(name="tgv_step", **gt.CFG))
+    guess = np.zeros_like(g["Pp_1"])
+    for step in (1, 2):
+        rhs = np.ascontiguousarray(g["mgRHS_%d" % step])
+        p_ref = guess.copy()
+        ref = o.mg_solve([p_ref], [rhs.copy()])
+        for mode in ("injected_mean", "natural"):
+            s.debug_set_rhs_mean(mode == "injected_mean", o.last_global_avg())
+            p_got = guess.copy()
+            got = s.mg_solve(p_got, rhs.copy())
+            assert got["cycles"] == ref["cycles"]
+            assert np.array_equal(got["coarse_iters"], ref["coarse_iters"])
+            for a, b in zip(got["residuals"], ref["residuals"]):
+                assert abs(a - b) <= 1e-10 * abs(b) + 1e-300
+            if mode == "injected_mean":
+                assert np.array_equal(p_got, p_ref), max_abs(p_got - p_ref)
+                assert np.array_equal(p_got[1:-1, 1:-1, 1:-1], g["Pp_%d" % step][1:-1, 1:-1, 1:-1])      # ... which is the reference's own Pp
+            else:
+                check_natural_mean_field(o, [guess], [rhs], 0, p_got, [p_ref], "tgv step %d" % step)
+        guess = np.ascontiguousarray(g["Pp_%d" % step])
+    s.close()
