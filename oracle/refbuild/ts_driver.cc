@@ -4,8 +4,8 @@
  * an execution of the reference itself.
  *
  * Linked into oracle/_ref/libsarasts_d3.so with the reference's UNMODIFIED sources, compiled from where they lie under
- * /root/reference: src/solvers/hydro/{hydro,hydro_d3}.cc, lib/field/*.cc, lib/boundary/*.cc (but hotPlateCC.cc, a scalar-solver
- * class), lib/force/*.cc, lib/initial/*.cc, lib/io/{parser,tseries}.cc, lib/parallel/{parallel,mpidata}.cc, lib/grid/grid.cc,
+ * /root/reference: src/solvers/hydro/{hydro,hydro_d3}.cc, src/solvers/scalar/{scalar,scalar_d3}.cc, lib/field/*.cc,
+ * lib/boundary/*.cc, lib/force/*.cc, lib/initial/*.cc, lib/io/{parser,tseries}.cc, lib/parallel/{parallel,mpidata}.cc, lib/grid/grid.cc,
  * lib/poisson/*.cc -- against the stand-in Blitz / MPI / yaml-cpp headers of saras_b200/host/compat.  The HDF5-backed classes
  * (writer, reader, probes) are not built: standin_ts/hdf5.h lets their headers parse, and this file defines the members the
  * time stepper references as do-nothing functions (none is called here: no solvePDE, no restart).
@@ -30,6 +30,7 @@
 #define protected public            /* the pieces of hydro_d3 called below are protected members; the sources stay unmodified */
 #define private public
 #include "hydro.h"
+#include "scalar.h"
 #undef protected
 #undef private
 
@@ -58,10 +59,13 @@ typedef struct {
     int icType;             /* "Initial Condition": 0 zero, 1 Taylor-Green vortex, 2 / 3 channel profiles (hydro_d3.cc:88-101) */
     int nSteps;             /* mode 7: number of timeAdvance() calls */
     int outputOnly;         /* bit q set: field q of ts_rank_fields is only written (the constructor's / initial condition's value is kept as input) */
+    int solverKind;         /* 0 hydro_d3, 1 scalar_d3 (Rayleigh-Benard: Problem Type 5-8) */
+    int rbcType, forceType; /* "RBC Type" (non-dimensionalisation, scalar.cc:70-86), "Force" (scalar.cc:131-156: 0 none, 1 random, 2 Coriolis, 3 buoyancy, 4 rotating convection) */
+    double Ra, Pr;
 } ts_params;
 
-/* per rank: Vx, Vy, Vz, P, Pp, mgRHS, nseRHS.Vx, nseRHS.Vy, nseRHS.Vz (any may be NULL: left as the constructor set it) */
-typedef struct { double *f[9]; } ts_rank_fields;
+/* per rank: Vx, Vy, Vz, P, Pp, mgRHS, nseRHS.Vx, nseRHS.Vy, nseRHS.Vz, T (any may be NULL: left as the constructor set it; T: scalar_d3 only) */
+typedef struct { double *f[10]; } ts_rank_fields;
 
 }
 
@@ -77,10 +81,10 @@ void write_yaml(const ts_params &p, const std::string &dir) {
     char mesh[4] = {p.xGrid == 2 ? 'D' : 'U', p.yGrid == 2 ? 'D' : 'U', p.zGrid == 2 ? 'D' : 'U', 0};
     f.precision(17);
     f << "\"Program\":\n"
-      << "    \"Problem Type\": " << p.probType << "\n    \"Initial Condition\": " << p.icType << "\n    \"Domain Type\": \"" << dom << "\"\n    \"RBC Type\": 1\n"
-      << "    \"Reynolds Number\": " << p.Re << "\n    \"Rossby Number\": 12\n    \"Rayleigh Number\": 10000\n    \"Prandtl Number\": 0.71\n"
+      << "    \"Problem Type\": " << p.probType << "\n    \"Initial Condition\": " << p.icType << "\n    \"Domain Type\": \"" << dom << "\"\n    \"RBC Type\": " << (p.rbcType ? p.rbcType : 1) << "\n"
+      << "    \"Reynolds Number\": " << p.Re << "\n    \"Rossby Number\": 12\n    \"Rayleigh Number\": " << (p.Ra > 0 ? p.Ra : 10000.0) << "\n    \"Prandtl Number\": " << (p.Pr > 0 ? p.Pr : 0.71) << "\n"
       << "    \"Taylor Number\": 0.0\n    \"X Length\": " << p.Lx << "\n    \"Y Length\": " << p.Ly << "\n    \"Z Length\": " << p.Lz << "\n"
-      << "    \"Heating Plate\": false\n    \"Plate Radius\": 0.25\n    \"Force\": 0\n"
+      << "    \"Heating Plate\": false\n    \"Plate Radius\": 0.25\n    \"Force\": " << p.forceType << "\n"
       << "\"Mesh\":\n    \"Mesh Type\": \"" << mesh << "\"\n    \"X Beta\": " << p.betaX << "\n    \"Y Beta\": " << p.betaY << "\n    \"Z Beta\": " << p.betaZ << "\n"
       << "    \"X Index\": " << p.xInd << "\n    \"Y Index\": " << p.yInd << "\n    \"Z Index\": " << p.zInd << "\n"
       << "\"Parallel\":\n    \"Number of OMP threads\": 1\n    \"X Number of Procs\": " << p.npX << "\n    \"Y Number of Procs\": " << p.npY << "\n"
@@ -96,17 +100,14 @@ void write_yaml(const ts_params &p, const std::string &dir) {
 void put(blitz::Array<real, 3> &A, const double *src) { if (src) memcpy(A.dataFirst(), src, A.size() * sizeof(double)); }
 void get(const blitz::Array<real, 3> &A, double *dst) { if (dst) memcpy(dst, A.dataFirst(), A.size() * sizeof(double)); }
 
-void rank_main(void *arg) {
-    Job *job = (Job *)arg;
+template <class SOLVER>
+void run_solver(Job *job, const grid &gridData, const parser &inputParams, parallel &mpi, blitz::Array<real, 3> *(*extra)(SOLVER &)) {
     const ts_params &p = *job->prm;
-    parser inputParams;                          /* reads ./input/parameters.yaml */
-    parallel mpi(inputParams);
-    grid gridData(inputParams, mpi);
-    hydro_d3 H(gridData, inputParams, mpi);      /* P = 1, zero initial condition, checkPeriodic, initVBC, imposeU/V/WBCs */
-    H.dt = p.dt;                                 /* hydro_d3::solvePDE sets dt = inputParams.tStp (hydro_d3.cc:157); set here as no solvePDE runs */
+    SOLVER H(gridData, inputParams, mpi);        /* P = 1, initial condition, checkPeriodic, initVBC (initTBC), imposeU/V/W(T)BCs */
+    H.dt = p.dt;                                 /* solvePDE sets dt = inputParams.tStp (hydro_d3.cc:157); set here as no solvePDE runs */
     ts_rank_fields &F = job->flds[mpi.rank];
-    blitz::Array<real, 3> *dst[9] = {&H.V.Vx.F, &H.V.Vy.F, &H.V.Vz.F, &H.P.F.F, &H.Pp.F, &H.mgRHS.F, &H.nseRHS.Vx, &H.nseRHS.Vy, &H.nseRHS.Vz};
-    for (int q = 0; q < 9; q++) if (!((p.outputOnly >> q) & 1)) put(*dst[q], F.f[q]);
+    blitz::Array<real, 3> *dst[10] = {&H.V.Vx.F, &H.V.Vy.F, &H.V.Vz.F, &H.P.F.F, &H.Pp.F, &H.mgRHS.F, &H.nseRHS.Vx, &H.nseRHS.Vy, &H.nseRHS.Vz, extra(H)};
+    for (int q = 0; q < 10; q++) if (dst[q] && !((p.outputOnly >> q) & 1)) put(*dst[q], F.f[q]);
     const int m = job->mode;
     if (m == 6) { H.nseRHS = 0.0; H.V.computeDiff(H.nseRHS); }
     if (m == 7) for (int n = 0; n < p.nSteps; n++) H.timeAdvance();
@@ -121,22 +122,31 @@ void rank_main(void *arg) {
         H.V -= H.pressureGradient;
     }
     if (m == 2 || m == 4) { H.imposeUBCs(); H.imposeVBCs(); H.imposeWBCs(); }
-    get(H.V.Vx.F, F.f[0]); get(H.V.Vy.F, F.f[1]); get(H.V.Vz.F, F.f[2]);
-    get(H.P.F.F, F.f[3]); get(H.Pp.F, F.f[4]); get(H.mgRHS.F, F.f[5]);
-    get(H.nseRHS.Vx, F.f[6]); get(H.nseRHS.Vy, F.f[7]); get(H.nseRHS.Vz, F.f[8]);
+    for (int q = 0; q < 10; q++) if (dst[q]) get(*dst[q], F.f[q]);
+}
+blitz::Array<real, 3> *no_extra(hydro_d3 &) { return nullptr; }
+blitz::Array<real, 3> *temperature(scalar_d3 &S) { return &S.T.F.F; }
+
+void rank_main(void *arg) {
+    Job *job = (Job *)arg;
+    parser inputParams;                          /* reads ./input/parameters.yaml */
+    parallel mpi(inputParams);
+    grid gridData(inputParams, mpi);
+    if (job->prm->solverKind == 1) run_solver<scalar_d3>(job, gridData, inputParams, mpi, temperature);
+    else run_solver<hydro_d3>(job, gridData, inputParams, mpi, no_extra);
 }
 
 }  // namespace
 
 extern "C" {
 
-/* padded extents of the nine fields of one rank, in the order of ts_rank_fields (9 x 3 ints) */
+/* padded extents of the ten fields of one rank, in the order of ts_rank_fields (10 x 3 ints) */
 void sarasts_extents(const ts_params *p, int *out) {
     const int n[3] = {(1 << p->xInd) / p->npX + 1, (1 << p->yInd) / p->npY + 1, (1 << p->zInd) + 1};
     const int sc[3] = {n[0] + 2, n[1] + 2, n[2] + 2};
     const int vx[3] = {n[0] + 1, n[1] + 2, n[2] + 2}, vy[3] = {n[0] + 2, n[1] + 1, n[2] + 2}, vz[3] = {n[0] + 2, n[1] + 2, n[2] + 1};
-    const int *all[9] = {vx, vy, vz, sc, sc, sc, vx, vy, vz};
-    for (int q = 0; q < 9; q++) for (int d = 0; d < 3; d++) out[3 * q + d] = all[q][d];
+    const int *all[10] = {vx, vy, vz, sc, sc, sc, vx, vy, vz, sc};
+    for (int q = 0; q < 10; q++) for (int d = 0; d < 3; d++) out[3 * q + d] = all[q][d];
 }
 
 int sarasts_run(const char *workdir, const ts_params *prm, ts_rank_fields *flds, int mode) {

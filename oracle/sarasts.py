@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "libsarasts_d3.so")
 DIVERGENCE, CORRECTION, IMPOSE_BCS, IMPLICIT, STEP_TAIL, MGSOLVE, COMPUTE_DIFF, TIME_ADVANCE = range(8)
-FIELDS = ("vx", "vy", "vz", "P", "Pp", "mgRHS", "rhs_x", "rhs_y", "rhs_z")
+FIELDS = ("vx", "vy", "vz", "P", "Pp", "mgRHS", "rhs_x", "rhs_y", "rhs_z", "T")
 
 
 class TsParams(C.Structure):
@@ -18,11 +18,12 @@ class TsParams(C.Structure):
                [(k, C.c_double) for k in ("betaX", "betaY", "betaZ", "Lx", "Ly", "Lz")] + \
                [(k, C.c_int) for k in ("vcDepth", "vcCount", "preSmooth", "postSmooth", "gsSmooth", "resType")] + \
                [("mgTolerance", C.c_double), ("probType", C.c_int), ("Re", C.c_double), ("dt", C.c_double), ("cnTolerance", C.c_double),
-                ("icType", C.c_int), ("nSteps", C.c_int), ("outputOnly", C.c_int)]
+                ("icType", C.c_int), ("nSteps", C.c_int), ("outputOnly", C.c_int), ("solverKind", C.c_int), ("rbcType", C.c_int),
+                ("forceType", C.c_int), ("Ra", C.c_double), ("Pr", C.c_double)]
 
 
 class RankFields(C.Structure):
-    _fields_ = [("f", C.POINTER(C.c_double) * 9)]
+    _fields_ = [("f", C.POINTER(C.c_double) * 10)]
 
 
 def available():
@@ -42,7 +43,8 @@ def _load():
     return _lib
 
 
-def params(cfg, prob_type=1, Re=1000.0, dt=0.01, cn_tolerance=1e-6, ic_type=0, n_steps=1, output_only=()):
+def params(cfg, prob_type=1, Re=1000.0, dt=0.01, cn_tolerance=1e-6, ic_type=0, n_steps=1, output_only=(), scalar=False, rbc_type=2,
+           force_type=0, Ra=1.0e4, Pr=0.71):
     """cfg: an Oracle.cfg dictionary (oracle/mgoracle.py)"""
     p = TsParams()
     for k, _ in TsParams._fields_:
@@ -51,11 +53,12 @@ def params(cfg, prob_type=1, Re=1000.0, dt=0.01, cn_tolerance=1e-6, ic_type=0, n
     p.probType, p.Re, p.dt, p.cnTolerance = int(prob_type), float(Re), float(dt), float(cn_tolerance)
     p.icType, p.nSteps = int(ic_type), int(n_steps)
     p.outputOnly = sum(1 << FIELDS.index(name) for name in output_only)      # these fields keep the reference's own initial values
+    p.solverKind, p.rbcType, p.forceType, p.Ra, p.Pr = int(bool(scalar)), int(rbc_type), int(force_type), float(Ra), float(Pr)
     return p
 
 
 def extents(p):
-    out = (C.c_int * 27)()
+    out = (C.c_int * 30)()
     _load().sarasts_extents(C.byref(p), out)
     return {name: tuple(out[3 * q:3 * q + 3]) for q, name in enumerate(FIELDS)}
 

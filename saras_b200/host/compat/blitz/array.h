@@ -400,6 +400,16 @@ class Array {
         forEachIndex([&](const int *p) { r.atPos(p) = f(atPos(p), o.atPos(p)); });
         return r;
     }
+    /* the same with an operand of another element type (e.g. a bool mask) */
+    template <class U, class F>
+    Array zipOther(const Array<U, N> &o, F f) const {
+        assert(sameShape(o.ext_));
+        Array r;
+        int b[N]; for (int d = 0; d < N; d++) b[d] = base_[d];
+        r.setup(ext_, b);
+        forEachIndex([&](const int *p) { r.atPos(p) = f(atPos(p), o.atPos(p)); });
+        return r;
+    }
     /* sequential reduction in storage (row-major) order */
     template <class Acc, class F>
     Acc fold(Acc init, F f) const {
@@ -432,6 +442,8 @@ SARAS_ARR_BINOP(-)
 SARAS_ARR_BINOP(*)
 SARAS_ARR_BINOP(/)
 #undef SARAS_ARR_BINOP
+template <class T, class U, int N, typename std::enable_if<!std::is_same<T, U>::value, int>::type = 0>
+Array<T, N> operator*(const Array<T, N> &a, const Array<U, N> &m) { return a.zipOther(m, [](const T &x, const U &y) { return x * T(y); }); }
 template <class T, int N> Array<T, N> fabs(const Array<T, N> &a) { return a.map([](const T &x) { return T(std::fabs(x)); }); }
 template <class T, int N> Array<T, N> abs(const Array<T, N> &a) { return a.map([](const T &x) { return T(std::fabs(x)); }); }
 template <class T, int N> Array<T, N> sqrt(const Array<T, N> &a) { return a.map([](const T &x) { return T(std::sqrt(x)); }); }

@@ -415,16 +415,18 @@ def test_fused_residual_restriction_equals_two_passes(case, monkeypatch):
     assert launches[0] != launches[1], launches
 
 
-def test_mg_solve_on_captured_time_step_rhs():
+@pytest.mark.parametrize("fixture", ["tgv_step_33", "rbc_step_33"])
+def test_mg_solve_on_captured_time_step_rhs(fixture):
     """BASELINE config C3's problem with REAL right-hand sides: tests/golden/tgv_step_33.npz holds mgRHS = div(V*) / dt of two
     consecutive hydro_d3::timeAdvance() calls of the Taylor-Green vortex (Re 1600, periodic 2 pi box, Gauss-Seidel multigrid) as the
     reference's own time stepper formed them, and the Pp it was left with (tests/golden/make_golden_timestep.py;
     tests/test_reference_timestep.py pins the oracle on them).  Same bar as test_mg_solve_parity, Pp of step 1 being the initial
-    guess of step 2 as in the time stepper."""
+    guess of step 2 as in the time stepper.  rbc_step_33: the same from scalar_d3::timeAdvance() for config C4's problem (Rayleigh-Benard,
+    Ra 1e8, tanh-stretched z between the plates)."""
     import os
     from tests.golden import make_golden_timestep as gt
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tgv_step_33.npz"))
-    o, s = _mk(dict(name="tgv_step", **gt.CFG))
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fixture + ".npz"))
+    o, s = _mk(dict(name=fixture, **gt.CASES[fixture][0]))
     guess = np.zeros_like(g["Pp_1"])
     for step in (1, 2):
         rhs = np.ascontiguousarray(g["mgRHS_%d" % step])
@@ -442,6 +444,6 @@ def test_mg_solve_on_captured_time_step_rhs():
                 assert np.array_equal(p_got, p_ref), max_abs(p_got - p_ref)
                 assert np.array_equal(p_got[1:-1, 1:-1, 1:-1], g["Pp_%d" % step][1:-1, 1:-1, 1:-1])      # ... which is the reference's own Pp
             else:
-                check_natural_mean_field(o, [guess], [rhs], 0, p_got, [p_ref], "tgv step %d" % step)
+                check_natural_mean_field(o, [guess], [rhs], 0, p_got, [p_ref], "%s step %d" % (fixture, step))
         guess = np.ascontiguousarray(g["Pp_%d" % step])
     s.close()

@@ -83,12 +83,13 @@ def test_reference_taylor_green_steps_are_physical():
     assert abs(decay - np.exp(-2.0 * nu * 3.0 * 3 * dt)) < 2e-4, decay
 
 
-def test_multigrid_oracle_reproduces_the_captured_time_steps():
-    """tests/golden/tgv_step_33.npz (two timeAdvance() calls of the reference, tests/golden/make_golden_timestep.py): from the
-    right-hand side the time stepper formed and the previous Pp as initial guess, the multigrid oracle + Pp.syncData() must
+@pytest.mark.parametrize("case", sorted(gt.CASES))
+def test_multigrid_oracle_reproduces_the_captured_time_steps(case):
+    """tests/golden/{tgv,rbc}_step_33.npz (two timeAdvance() calls of the reference each, tests/golden/make_golden_timestep.py): from
+    the right-hand side the time stepper formed and the previous Pp as initial guess, the multigrid oracle + Pp.syncData() must
     give the Pp the reference was left with, bit for bit"""
-    g = np.load(os.path.join(HERE, "golden", "tgv_step_33.npz"))
-    o = Oracle(**gt.CFG)
+    g = np.load(os.path.join(HERE, "golden", case + ".npz"))
+    o = Oracle(**gt.CASES[case][0])
     pp = np.zeros_like(g["Pp_1"])
     for step in (1, 2):
         o.mg_solve([pp], [np.ascontiguousarray(g["mgRHS_%d" % step])])
@@ -97,7 +98,8 @@ def test_multigrid_oracle_reproduces_the_captured_time_steps():
 
 
 @needs_ts
-def test_time_step_fixture_is_what_the_reference_produces_now():
-    g = np.load(os.path.join(HERE, "golden", "tgv_step_33.npz"))
-    r = gt.reference_steps(2)
+@pytest.mark.parametrize("case", sorted(gt.CASES))
+def test_time_step_fixture_is_what_the_reference_produces_now(case):
+    g = np.load(os.path.join(HERE, "golden", case + ".npz"))
+    r = gt.reference_steps(2, case)
     assert np.array_equal(r["mgRHS"], g["mgRHS_2"]) and np.array_equal(r["Pp"], g["Pp_2"])
