@@ -17,7 +17,8 @@
  * sources compiled by oracle/refbuild/Makefile, driven by oracle/refbuild/ts_driver.cc) and requires this file to reproduce
  * the resulting velocity fields BIT FOR BIT -- lid-driven cavity, channel, fully periodic and inflow / outflow boundary sets,
  * uniform and tanh meshes, alone and chained with the projection step.  The squared metrics are pinned against the reference's
- * grid object (tests/test_impl_oracle.py).  One rank only.
+ * grid object (tests/test_impl_oracle.py).  One rank (implo_solve), npX x npY ranks (implo_solve_multi), and the scalar solver's
+ * temperature solve (implo_solve_T, one rank).
  *
  * A velocity component is a Blitz array with base index -1, z fastest: extent of a direction = core size + 2, where the core
  * has n points if the component is staggered (cell-centred) there and n - 1 if it is collocated (face-centred): Vx is
@@ -158,4 +159,185 @@ int implo_solve(const implo_params *p, int comp, double *V, const double *rhs, d
  * Pinned bit for bit against the reference's grid object in tests/test_impl_oracle.py. */
 void implo_metric2(int count, const double *m1, double *out) {
     for (int q = 0; q < count; q++) out[q] = pow(m1[q], 2.0);
+}
+
+/* ---- several ranks (npX x npY pencils, all emulated in one process; rank = yRank * npX + xRank) ---------------------------------
+ * What changes against one rank: the bulk is cut only on the ranks that own a wall (field.cc:206-212), syncData exchanges faces
+ * with the neighbouring ranks (periodic wrap; MPI_PROC_NULL at the walls of a non-periodic direction, hydro.cc:174-203) and
+ * edges with the diagonal ranks (always the periodic wrap, parallel.cc:124-129), the wall objects act only where rankFlag is set
+ * (boundary.cc:57-73), and maxError is the MPI_MAX over ranks (plainvf.h:97-105).  Pinned like the one-rank version
+ * (tests/test_oracle_vs_timestepper.py, 2x1 / 2x2 / 1x2 ranks). */
+static void implo_geometry_rank(const implo_params *p, int comp, int npX, int npY, int r, implo_geom *g) {
+    const int xr = r % npX, yr = r / npX;
+    const int first[3] = {xr == 0, yr == 0, 1}, last[3] = {xr == npX - 1, yr == npY - 1, 1};
+    for (int d = 0; d < 3; d++) {
+        g->stag[d] = (d != comp);
+        g->cs[d] = g->stag[d] ? p->n[d] : p->n[d] - 1;
+        g->ext[d] = g->cs[d] + 2;
+        const int cut = g->stag[d] && !p->per[d];
+        g->lb[d] = (cut && first[d]) ? 1 : 0;
+        g->ub[d] = g->cs[d] - 1 - ((cut && last[d]) ? 1 : 0);
+    }
+}
+static int implo_rank_of(int xr, int yr, int npX, int npY) { return ((yr + npY) % npY) * npX + ((xr + npX) % npX); }
+
+/* imposeUBCs / VBCs / WBCs on all ranks: F[r] is rank r's array (all ranks share the extents: equal pencils) */
+void implo_impose_bcs_multi(const implo_params *p, int comp, int npX, int npY, double *const *F) {
+    const int nr = npX * npY;
+    implo_geom G0, *g = &G0;
+    implo_geometry_rank(p, comp, npX, npY, 0, g);          /* extents and staggering do not depend on the rank */
+    const int ox = g->stag[0] ? 1 : 0, oy = g->stag[1] ? 1 : 0, cx = g->cs[0], cy = g->cs[1], cz = g->cs[2];
+    /* faces: every message is read from core points and lands in a pad, so the order does not matter */
+    for (int r = 0; r < nr; r++) {
+        const int xr = r % npX, yr = r / npX;
+        double *D = F[r];
+        if (p->per[0] || xr > 0) { const double *S = F[implo_rank_of(xr - 1, yr, npX, npY)];
+            for (int j = 0; j < cy; j++) for (int k = 0; k < cz; k++) D[AT(g, -1, j, k)] = S[AT(g, cx - 1 - ox, j, k)]; }
+        if (p->per[0] || xr < npX - 1) { const double *S = F[implo_rank_of(xr + 1, yr, npX, npY)];
+            for (int j = 0; j < cy; j++) for (int k = 0; k < cz; k++) D[AT(g, cx, j, k)] = S[AT(g, ox, j, k)]; }
+        if (p->per[1] || yr > 0) { const double *S = F[implo_rank_of(xr, yr - 1, npX, npY)];
+            for (int i = 0; i < cx; i++) for (int k = 0; k < cz; k++) D[AT(g, i, -1, k)] = S[AT(g, i, cy - 1 - oy, k)]; }
+        if (p->per[1] || yr < npY - 1) { const double *S = F[implo_rank_of(xr, yr + 1, npX, npY)];
+            for (int i = 0; i < cx; i++) for (int k = 0; k < cz; k++) D[AT(g, i, cy, k)] = S[AT(g, i, oy, k)]; }
+    }
+    for (int r = 0; r < nr; r++) {
+        const int xr = r % npX, yr = r / npX;
+        double *D = F[r];
+        for (int xh = 0; xh < 2; xh++) for (int yh = 0; yh < 2; yh++) {
+            const double *S = F[implo_rank_of(xr + (xh ? 1 : -1), yr + (yh ? 1 : -1), npX, npY)];
+            for (int k = 0; k < cz; k++) D[AT(g, xh ? cx : -1, yh ? cy : -1, k)] = S[AT(g, xh ? ox : cx - 1 - ox, yh ? oy : cy - 1 - oy, k)];
+        }
+    }
+    /* wall objects: left, right, front, back, top, bottom on the ranks whose rankFlag is set */
+    const int order[6] = {0, 1, 2, 3, 5, 4};
+    for (int r = 0; r < nr; r++) {
+        const int xr = r % npX, yr = r / npX;
+        implo_geom GR, *gr = &GR;
+        implo_geometry_rank(p, comp, npX, npY, r, gr);
+        for (int q = 0; q < 6; q++) {
+            const int w = order[q], ax = w / 2, hi = w & 1;
+            const int t = p->bc_type[w];
+            if (t == IMPL_BC_NONE) continue;
+            const int flag = (w == 0) ? (xr == 0) : (w == 1) ? (xr == npX - 1) : (w == 2) ? (yr == 0) : (w == 3) ? (yr == npY - 1) : 1;
+            if (!flag && t != IMPL_BC_PERIODIC_CC && t != IMPL_BC_PERIODIC_FC) continue;     /* the periodic classes ignore rankFlag */
+            const int wall_lo = gr->lb[ax] - 1, wall_hi = gr->ub[ax] + 1;
+            const int dst = hi ? wall_hi : wall_lo;
+            int src = dst + (hi ? -1 : 1);
+            if (t == IMPL_BC_PERIODIC_CC) src = hi ? wall_lo + 2 : wall_hi - 2;
+            if (t == IMPL_BC_PERIODIC_FC) src = hi ? wall_lo + 1 : wall_hi - 1;
+            implo_plane(F[r], gr, ax, dst, src, t, p->bc_value[w]);
+        }
+    }
+}
+
+/* solveVx / Vy / Vz on all ranks.  Returns the number of sweeps (the same on every rank: the test is global), -1 on overflow. */
+int implo_solve_multi(const implo_params *p, int comp, int npX, int npY, double *const *V, const double *const *rhs,
+                      const double *const *m2c_x, const double *const *m2s_x, const double *const *m2c_y, const double *const *m2s_y,
+                      double *max_err) {
+    const int nr = npX * npY;
+    implo_geom G0;
+    implo_geometry_rank(p, comp, npX, npY, 0, &G0);
+    const size_t tot = (size_t)G0.ext[0] * G0.ext[1] * G0.ext[2];
+    double **guess = (double **)malloc(sizeof(double *) * nr);
+    for (int r = 0; r < nr; r++) guess[r] = (double *)calloc(tot, sizeof(double));
+    const double hx = p->dXi, hy = p->dEt, hz = p->dZt;
+    const double hz2hx2 = pow(p->dZt, 2.0) * pow(p->dXi, 2.0), hx2hy2 = pow(p->dXi, 2.0) * pow(p->dEt, 2.0), hy2hz2 = pow(p->dEt, 2.0) * pow(p->dZt, 2.0);
+    const double hx2hy2hz2 = pow(p->dXi, 2.0) * pow(p->dEt, 2.0) * pow(p->dZt, 2.0);
+    const double inverseRe = 1.0 / p->Re, dt = p->dt, Re = p->Re;
+    const long long maxIterations = (long long)(p->n[0] - 1) * (p->n[1] - 1) * (p->n[2] - 1);
+    const double *mz = (G0.stag[2] ? p->m2s[2] : p->m2c[2]) + 1;
+    int iterCount = 0;
+    double maxError = 0.0;
+    for (;;) {
+        for (int r = 0; r < nr; r++) {
+            implo_geom G, *g = &G;
+            implo_geometry_rank(p, comp, npX, npY, r, g);
+            const double *mx = (g->stag[0] ? m2s_x[r] : m2c_x[r]) + 1, *my = (g->stag[1] ? m2s_y[r] : m2c_y[r]) + 1;
+            const double *v = V[r], *b = rhs[r];
+            for (int i = g->lb[0]; i <= g->ub[0]; i++) for (int j = g->lb[1]; j <= g->ub[1]; j++) for (int k = g->lb[2]; k <= g->ub[2]; k++)
+                guess[r][AT(g, i, j, k)] = ((hy2hz2 * mx[i] * (v[AT(g, i + 1, j, k)] + v[AT(g, i - 1, j, k)]) +
+                                             hz2hx2 * my[j] * (v[AT(g, i, j + 1, k)] + v[AT(g, i, j - 1, k)]) +
+                                             hx2hy2 * mz[k] * (v[AT(g, i, j, k + 1)] + v[AT(g, i, j, k - 1)])) *
+                                            dt / (hx2hy2hz2 * 2.0 * Re) + b[AT(g, i, j, k)]) /
+                                           (1.0 + dt * ((hy2hz2 * mx[i] + hz2hx2 * my[j] + hx2hy2 * mz[k])) / (Re * hx2hy2hz2));
+        }
+        for (int r = 0; r < nr; r++) memcpy(V[r], guess[r], tot * sizeof(double));
+        implo_impose_bcs_multi(p, comp, npX, npY, V);
+        maxError = 0.0;
+        for (int r = 0; r < nr; r++) {
+            implo_geom G, *g = &G;
+            implo_geometry_rank(p, comp, npX, npY, r, g);
+            const double *mx = (g->stag[0] ? m2s_x[r] : m2c_x[r]) + 1, *my = (g->stag[1] ? m2s_y[r] : m2c_y[r]) + 1;
+            const double *v = V[r], *b = rhs[r];
+            for (int i = g->lb[0]; i <= g->ub[0]; i++) for (int j = g->lb[1]; j <= g->ub[1]; j++) for (int k = g->lb[2]; k <= g->ub[2]; k++) {
+                const double c = v[AT(g, i, j, k)];
+                const double lap = c - (mx[i] * (v[AT(g, i + 1, j, k)] - 2.0 * c + v[AT(g, i - 1, j, k)]) / (hx * hx) +
+                                        my[j] * (v[AT(g, i, j + 1, k)] - 2.0 * c + v[AT(g, i, j - 1, k)]) / (hy * hy) +
+                                        mz[k] * (v[AT(g, i, j, k + 1)] - 2.0 * c + v[AT(g, i, j, k - 1)]) / (hz * hz)) *
+                                           0.5 * dt * inverseRe;
+                const double e = fabs(lap - b[AT(g, i, j, k)]);
+                if (e > maxError) maxError = e;
+            }
+        }
+        if (maxError < p->tol) break;
+        iterCount += 1;
+        if (iterCount > maxIterations) { iterCount = -2; break; }
+    }
+    for (int r = 0; r < nr; r++) free(guess[r]);
+    free(guess);
+    if (max_err) *max_err = maxError;
+    return iterCount + 1;
+}
+
+/* ---- scalar_d3::solveT (src/solvers/scalar/scalar_d3.cc:541-594), one rank ---------------------------------------------------------
+ * NOT the velocity expression with other names: the diffusivity kappa multiplies inside (`* dt * kappa / (hx2hy2hz2 * 2.0)`,
+ * `1.0 + dt * kappa * (...) / hx2hy2hz2`, `* 0.5 * dt * kappa`), the z metric is ztz2COLLOC although T is staggered in z
+ * (scalar_d3.cc:551, 555, 570: replicated, not fixed), the boundary objects are those of scalar::initTBC (scalar.cc:186-229)
+ * imposed in the order left, right, front, back, top, bottom (scalar.cc:240-255), and the max runs over the collocated index
+ * ranges of plainsf::fxMax (plainsf.h:123-131), i.e. without the last staggered point of a periodic direction.
+ * p: comp is ignored (T is staggered in every direction); bc_type / bc_value describe T's walls; Re holds 1 / kappa is NOT
+ * used -- kappa is passed explicitly. */
+int implo_solve_T(const implo_params *p, double kappa, double *T, const double *rhs, double *max_err) {
+    implo_geom G, *g = &G;
+    implo_geometry(p, 3, g);                                            /* comp = 3: no collocated direction */
+    const size_t tot = (size_t)g->ext[0] * g->ext[1] * g->ext[2];
+    double *guess = (double *)calloc(tot, sizeof(double));
+    const double hx = p->dXi, hy = p->dEt, hz = p->dZt;
+    const double hz2hx2 = pow(p->dZt, 2.0) * pow(p->dXi, 2.0), hx2hy2 = pow(p->dXi, 2.0) * pow(p->dEt, 2.0), hy2hz2 = pow(p->dEt, 2.0) * pow(p->dZt, 2.0);
+    const double hx2hy2hz2 = pow(p->dXi, 2.0) * pow(p->dEt, 2.0) * pow(p->dZt, 2.0);
+    const double dt = p->dt;
+    const double *mx = p->m2s[0] + 1, *my = p->m2s[1] + 1, *mz = p->m2c[2] + 1;       /* ztz2Colloc: indices -1 .. n-1 (n+1 entries) */
+    const long long maxIterations = (long long)(p->n[0] - 1) * (p->n[1] - 1) * (p->n[2] - 1);
+    int iterCount = 0;
+    double maxError = 0.0;
+    for (;;) {
+        for (int i = g->lb[0]; i <= g->ub[0]; i++) for (int j = g->lb[1]; j <= g->ub[1]; j++) for (int k = g->lb[2]; k <= g->ub[2]; k++)
+            guess[AT(g, i, j, k)] = ((hy2hz2 * mx[i] * (T[AT(g, i + 1, j, k)] + T[AT(g, i - 1, j, k)]) +
+                                      hz2hx2 * my[j] * (T[AT(g, i, j + 1, k)] + T[AT(g, i, j - 1, k)]) +
+                                      hx2hy2 * mz[k] * (T[AT(g, i, j, k + 1)] + T[AT(g, i, j, k - 1)])) *
+                                     dt * kappa / (hx2hy2hz2 * 2.0) + rhs[AT(g, i, j, k)]) /
+                                    (1.0 + dt * kappa * ((hy2hz2 * mx[i] + hz2hx2 * my[j] + hx2hy2 * mz[k])) / hx2hy2hz2);
+        memcpy(T, guess, tot * sizeof(double));                         /* T = guessedScalar (sfield.cc:284-286) */
+        {   /* imposeTBCs: the velocity routine with comp = 3 (all staggered) does exactly T.syncData() + the wall objects */
+            implo_params q = *p;
+            implo_impose_bcs(&q, 3, T);
+        }
+        maxError = 0.0;
+        for (int i = g->lb[0]; i <= g->ub[0]; i++) for (int j = g->lb[1]; j <= g->ub[1]; j++) for (int k = g->lb[2]; k <= g->ub[2]; k++) {
+            if (i > p->n[0] - 2 || j > p->n[1] - 2 || k > p->n[2] - 2) continue;        /* fxMax: F(xColl, yColl, zColl) */
+            const double c = T[AT(g, i, j, k)];
+            const double lap = c - (mx[i] * (T[AT(g, i + 1, j, k)] - 2.0 * c + T[AT(g, i - 1, j, k)]) / (hx * hx) +
+                                    my[j] * (T[AT(g, i, j + 1, k)] - 2.0 * c + T[AT(g, i, j - 1, k)]) / (hy * hy) +
+                                    mz[k] * (T[AT(g, i, j, k + 1)] - 2.0 * c + T[AT(g, i, j, k - 1)]) / (hz * hz)) *
+                                       0.5 * dt * kappa;
+            const double e = fabs(lap - rhs[AT(g, i, j, k)]);
+            if (e > maxError) maxError = e;
+        }
+        if (maxError < p->tol) break;
+        iterCount += 1;
+        if (iterCount > maxIterations) { free(guess); if (max_err) *max_err = maxError; return -1; }
+    }
+    free(guess);
+    if (max_err) *max_err = maxError;
+    return iterCount + 1;
 }

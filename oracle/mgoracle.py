@@ -95,6 +95,12 @@ def _load(fast=False):
     lib.implo_impose_bcs.argtypes = [C.POINTER(ImploParams), C.c_int, dp]
     lib.implo_solve.argtypes = [C.POINTER(ImploParams), C.c_int, dp, dp, dp]
     lib.implo_solve.restype = C.c_int
+    dpp_ = C.POINTER(dp)
+    lib.implo_impose_bcs_multi.argtypes = [C.POINTER(ImploParams), C.c_int, C.c_int, C.c_int, dpp_]
+    lib.implo_solve_multi.argtypes = [C.POINTER(ImploParams), C.c_int, C.c_int, C.c_int, dpp_, dpp_, dpp_, dpp_, dpp_, dpp_, dp]
+    lib.implo_solve_multi.restype = C.c_int
+    lib.implo_solve_T.argtypes = [C.POINTER(ImploParams), C.c_double, dp, dp, dp]
+    lib.implo_solve_T.restype = C.c_int
     lib.projo_correct_nosync.argtypes = [C.c_int] * 3 + [dp] * 8 + [C.c_double] * 4
     lib.mgo_lup_count.argtypes = [vp]
     _LIBS[key] = lib
@@ -377,3 +383,86 @@ class ImplOracle:
         e = C.c_double(0.0)
         n = self.lib.implo_solve(C.byref(self.params[comp]), comp, _dpp(V), _dpp(rhs), C.byref(e))
         return n, e.value
+
+
+class ImplOracleMulti:
+    """hydro_d3::solveVx / Vy / Vz and imposeUBCs / VBCs / WBCs on npX x npY ranks, all emulated in one process"""
+
+    def __init__(self, o, dt, Re, tol, bc_type, bc_value):
+        self.lib = _load()
+        self.o = o
+        self.n, _ = o.level_dims(0)
+        c = o.cfg
+        self.npx, self.npy = c["npX"], c["npY"]
+        self.m2 = [impl_metrics2(o, r) for r in range(o.nranks)]          # per rank: (colloc2[3], staggr2[3])
+        self.params = []
+        for comp in range(3):
+            p = ImploParams()
+            p.n[:] = self.n
+            p.per[:] = [int(c["xPer"]), int(c["yPer"]), int(c["zPer"])]
+            p.dt, p.Re, p.tol = float(dt), float(Re), float(tol)
+            p.dXi, p.dEt, p.dZt = o.spacing()
+            for d in range(3):
+                p.m2c[d] = _dpp(self.m2[0][0][d])
+                p.m2s[d] = _dpp(self.m2[0][1][d])
+            p.bc_type[:] = [int(v) for v in bc_type[comp]]
+            p.bc_value[:] = [float(v) for v in bc_value[comp]]
+            self.params.append(p)
+
+    def _ptrs(self, arrs):
+        dp = C.POINTER(C.c_double)
+        return (dp * len(arrs))(*[_dpp(a) for a in arrs])
+
+    def impose_bcs(self, comp, V_list):
+        self.lib.implo_impose_bcs_multi(C.byref(self.params[comp]), comp, self.npx, self.npy, self._ptrs(V_list))
+
+    def solve(self, comp, V_list, rhs_list):
+        e = C.c_double(0.0)
+        m = self.m2
+        n = self.lib.implo_solve_multi(C.byref(self.params[comp]), comp, self.npx, self.npy, self._ptrs(V_list), self._ptrs(rhs_list),
+                                       self._ptrs([x[0][0] for x in m]), self._ptrs([x[1][0] for x in m]),
+                                       self._ptrs([x[0][1] for x in m]), self._ptrs([x[1][1] for x in m]), C.byref(e))
+        return n, e.value
+
+
+def temperature_bcs(x_per, y_per, z_per, prob_type=5):
+    """scalar::initTBC (src/solvers/scalar/scalar.cc:186-229) without the heating-plate option: class codes as in impl_oracle.c"""
+    NONE, DCC, DFC, NEU, PCC, PFC = range(6)
+    t, v = [NONE] * 6, [0.0] * 6
+    if not x_per:
+        if prob_type == 7:
+            t[0], t[1], v[0] = DCC, DCC, 1.0
+        else:
+            t[0], t[1] = NEU, NEU
+    if not y_per:
+        t[2], t[3] = NEU, NEU
+    if z_per:
+        t[4], t[5] = PCC, PCC
+    else:
+        t[4], t[5] = DCC, DCC
+        if prob_type == 6:
+            v[5] = 1.0
+        else:
+            v[4] = 1.0
+    return t, v
+
+
+def solve_temperature(o, dt, kappa, tol, bc_type, bc_value, T, rhs):
+    """scalar_d3::solveT on one rank, in place on T; returns (sweeps, max_error)"""
+    lib = _load()
+    coll2, stag2 = impl_metrics2(o)
+    p = ImploParams()
+    n, _ = o.level_dims(0)
+    c = o.cfg
+    p.n[:] = n
+    p.per[:] = [int(c["xPer"]), int(c["yPer"]), int(c["zPer"])]
+    p.dt, p.Re, p.tol = float(dt), 1.0, float(tol)
+    p.dXi, p.dEt, p.dZt = o.spacing()
+    for d in range(3):
+        p.m2c[d] = _dpp(coll2[d])
+        p.m2s[d] = _dpp(stag2[d])
+    p.bc_type[:] = [int(x) for x in bc_type]
+    p.bc_value[:] = [float(x) for x in bc_value]
+    e = C.c_double(0.0)
+    nsw = lib.implo_solve_T(C.byref(p), float(kappa), _dpp(T), _dpp(rhs), C.byref(e))
+    return nsw, e.value

@@ -18,6 +18,7 @@
  *   mode 4  modes 3, 0, mgSolve, 1, 2 in sequence: the tail of timeAdvance from nseRHS on               :303-366
  *   mode 6  nseRHS = 0; V.computeDiff(nseRHS);  (returned in the nseRHS slots)                          :259-265
  *   mode 7  nSteps x timeAdvance() from the configured initial condition (inputs given replace it)      :254-367
+ *   mode 8  scalar_d3::solveT() on the given T and tmpRHS                                     scalar_d3.cc:541-594
  * Fields go in and out as the padded Blitz arrays of every rank.  Ranks are threads (mpi-lite).
  */
 #include <cstdio>
@@ -64,8 +65,8 @@ typedef struct {
     double Ra, Pr;
 } ts_params;
 
-/* per rank: Vx, Vy, Vz, P, Pp, mgRHS, nseRHS.Vx, nseRHS.Vy, nseRHS.Vz, T (any may be NULL: left as the constructor set it; T: scalar_d3 only) */
-typedef struct { double *f[10]; } ts_rank_fields;
+/* per rank: Vx, Vy, Vz, P, Pp, mgRHS, nseRHS.Vx, nseRHS.Vy, nseRHS.Vz, T, tmpRHS (any may be NULL: left as the constructor set it; T, tmpRHS: scalar_d3 only) */
+typedef struct { double *f[11]; } ts_rank_fields;
 
 }
 
@@ -101,15 +102,16 @@ void put(blitz::Array<real, 3> &A, const double *src) { if (src) memcpy(A.dataFi
 void get(const blitz::Array<real, 3> &A, double *dst) { if (dst) memcpy(dst, A.dataFirst(), A.size() * sizeof(double)); }
 
 template <class SOLVER>
-void run_solver(Job *job, const grid &gridData, const parser &inputParams, parallel &mpi, blitz::Array<real, 3> *(*extra)(SOLVER &)) {
+void run_solver(Job *job, const grid &gridData, const parser &inputParams, parallel &mpi, blitz::Array<real, 3> *(*extra)(SOLVER &, int), void (*solve_t)(SOLVER &)) {
     const ts_params &p = *job->prm;
     SOLVER H(gridData, inputParams, mpi);        /* P = 1, initial condition, checkPeriodic, initVBC (initTBC), imposeU/V/W(T)BCs */
     H.dt = p.dt;                                 /* solvePDE sets dt = inputParams.tStp (hydro_d3.cc:157); set here as no solvePDE runs */
     ts_rank_fields &F = job->flds[mpi.rank];
-    blitz::Array<real, 3> *dst[10] = {&H.V.Vx.F, &H.V.Vy.F, &H.V.Vz.F, &H.P.F.F, &H.Pp.F, &H.mgRHS.F, &H.nseRHS.Vx, &H.nseRHS.Vy, &H.nseRHS.Vz, extra(H)};
-    for (int q = 0; q < 10; q++) if (dst[q] && !((p.outputOnly >> q) & 1)) put(*dst[q], F.f[q]);
+    blitz::Array<real, 3> *dst[11] = {&H.V.Vx.F, &H.V.Vy.F, &H.V.Vz.F, &H.P.F.F, &H.Pp.F, &H.mgRHS.F, &H.nseRHS.Vx, &H.nseRHS.Vy, &H.nseRHS.Vz, extra(H, 0), extra(H, 1)};
+    for (int q = 0; q < 11; q++) if (dst[q] && !((p.outputOnly >> q) & 1)) put(*dst[q], F.f[q]);
     const int m = job->mode;
     if (m == 6) { H.nseRHS = 0.0; H.V.computeDiff(H.nseRHS); }
+    if (m == 8) solve_t(H);                                         /* scalar_d3::solveT(), scalar_d3.cc:541-594 */
     if (m == 7) for (int n = 0; n < p.nSteps; n++) H.timeAdvance();
     if (m == 3 || m == 4) { H.solveVx(); H.solveVy(); H.solveVz(); }
     if (m == 0 || m == 4) { H.V.divergence(H.mgRHS, H.P); H.mgRHS *= 1.0 / H.dt; }
@@ -122,18 +124,20 @@ void run_solver(Job *job, const grid &gridData, const parser &inputParams, paral
         H.V -= H.pressureGradient;
     }
     if (m == 2 || m == 4) { H.imposeUBCs(); H.imposeVBCs(); H.imposeWBCs(); }
-    for (int q = 0; q < 10; q++) if (dst[q]) get(*dst[q], F.f[q]);
+    for (int q = 0; q < 11; q++) if (dst[q]) get(*dst[q], F.f[q]);
 }
-blitz::Array<real, 3> *no_extra(hydro_d3 &) { return nullptr; }
-blitz::Array<real, 3> *temperature(scalar_d3 &S) { return &S.T.F.F; }
+blitz::Array<real, 3> *no_extra(hydro_d3 &, int) { return nullptr; }
+blitz::Array<real, 3> *temperature(scalar_d3 &S, int which) { return which ? &S.tmpRHS.F : &S.T.F.F; }
+void no_solve_t(hydro_d3 &) {}
+void do_solve_t(scalar_d3 &S) { S.solveT(); }
 
 void rank_main(void *arg) {
     Job *job = (Job *)arg;
     parser inputParams;                          /* reads ./input/parameters.yaml */
     parallel mpi(inputParams);
     grid gridData(inputParams, mpi);
-    if (job->prm->solverKind == 1) run_solver<scalar_d3>(job, gridData, inputParams, mpi, temperature);
-    else run_solver<hydro_d3>(job, gridData, inputParams, mpi, no_extra);
+    if (job->prm->solverKind == 1) run_solver<scalar_d3>(job, gridData, inputParams, mpi, temperature, do_solve_t);
+    else run_solver<hydro_d3>(job, gridData, inputParams, mpi, no_extra, no_solve_t);
 }
 
 }  // namespace
@@ -145,8 +149,8 @@ void sarasts_extents(const ts_params *p, int *out) {
     const int n[3] = {(1 << p->xInd) / p->npX + 1, (1 << p->yInd) / p->npY + 1, (1 << p->zInd) + 1};
     const int sc[3] = {n[0] + 2, n[1] + 2, n[2] + 2};
     const int vx[3] = {n[0] + 1, n[1] + 2, n[2] + 2}, vy[3] = {n[0] + 2, n[1] + 1, n[2] + 2}, vz[3] = {n[0] + 2, n[1] + 2, n[2] + 1};
-    const int *all[10] = {vx, vy, vz, sc, sc, sc, vx, vy, vz, sc};
-    for (int q = 0; q < 10; q++) for (int d = 0; d < 3; d++) out[3 * q + d] = all[q][d];
+    const int *all[11] = {vx, vy, vz, sc, sc, sc, vx, vy, vz, sc, sc};
+    for (int q = 0; q < 11; q++) for (int d = 0; d < 3; d++) out[3 * q + d] = all[q][d];
 }
 
 int sarasts_run(const char *workdir, const ts_params *prm, ts_rank_fields *flds, int mode) {

@@ -9,8 +9,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "libsarasts_d3.so")
-DIVERGENCE, CORRECTION, IMPOSE_BCS, IMPLICIT, STEP_TAIL, MGSOLVE, COMPUTE_DIFF, TIME_ADVANCE = range(8)
-FIELDS = ("vx", "vy", "vz", "P", "Pp", "mgRHS", "rhs_x", "rhs_y", "rhs_z", "T")
+DIVERGENCE, CORRECTION, IMPOSE_BCS, IMPLICIT, STEP_TAIL, MGSOLVE, COMPUTE_DIFF, TIME_ADVANCE, SOLVE_T = range(9)
+FIELDS = ("vx", "vy", "vz", "P", "Pp", "mgRHS", "rhs_x", "rhs_y", "rhs_z", "T", "rhs_T")
 
 
 class TsParams(C.Structure):
@@ -23,7 +23,7 @@ class TsParams(C.Structure):
 
 
 class RankFields(C.Structure):
-    _fields_ = [("f", C.POINTER(C.c_double) * 10)]
+    _fields_ = [("f", C.POINTER(C.c_double) * 11)]
 
 
 def available():
@@ -58,7 +58,7 @@ def params(cfg, prob_type=1, Re=1000.0, dt=0.01, cn_tolerance=1e-6, ic_type=0, n
 
 
 def extents(p):
-    out = (C.c_int * 30)()
+    out = (C.c_int * 33)()
     _load().sarasts_extents(C.byref(p), out)
     return {name: tuple(out[3 * q:3 * q + 3]) for q, name in enumerate(FIELDS)}
 

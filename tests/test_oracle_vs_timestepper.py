@@ -145,3 +145,48 @@ def test_tail_of_time_advance_matches_the_reference(case):
         assert np.array_equal(rhs[r], flds[r]["mgRHS"]), "mgRHS"
         for k in ("Pp", "P", "vx", "vy", "vz"):
             assert np.array_equal(m[k], flds[r][k]), (k, float(np.max(np.abs(m[k] - flds[r][k]))))
+
+
+@pytest.mark.parametrize("case", MULTI, ids=lambda c: c["name"])
+def test_multirank_velocity_bcs_and_implicit_solves_match_the_reference(case):
+    """the same on several ranks (oracle/impl_oracle.c, implo_*_multi): syncData of the velocity components between ranks (the
+    collocated direction sends plane 0 / n-1, the staggered ones 1 / n-2), wall objects on the ranks that own a wall, global MAX"""
+    dt, Re, tol = 0.02, 2.0, 1e-5
+    o, p = _mk(case, dt=dt, Re=Re, cn_tolerance=tol)
+    t, v = capi.velocity_bcs(o.cfg["xPer"], o.cfg["yPer"], o.cfg["zPer"], case["prob"])
+    io = mo.ImplOracleMulti(o, dt, Re, tol, t, v)
+    flds = _rand_fields(p, 6, ("vx", "vy", "vz"))
+    mine = [{k: a.copy() for k, a in d.items()} for d in flds]
+    sarasts.run(p, sarasts.IMPOSE_BCS, flds)
+    for comp, k in enumerate(("vx", "vy", "vz")):
+        io.impose_bcs(comp, [m[k] for m in mine])
+        for r in range(o.nranks):
+            assert np.array_equal(mine[r][k], flds[r][k]), ("bcs", k, r, float(np.max(np.abs(mine[r][k] - flds[r][k]))))
+    flds = _rand_fields(p, 7, ("vx", "vy", "vz", "rhs_x", "rhs_y", "rhs_z"))
+    mine = [{k: a.copy() for k, a in d.items()} for d in flds]
+    sarasts.run(p, sarasts.IMPLICIT, flds)
+    for comp, (k, rk) in enumerate((("vx", "rhs_x"), ("vy", "rhs_y"), ("vz", "rhs_z"))):
+        sweeps, err = io.solve(comp, [m[k] for m in mine], [m[rk] for m in mine])
+        assert sweeps > 2 and err < tol
+        for r in range(o.nranks):
+            assert np.array_equal(mine[r][k], flds[r][k]), ("solve", k, r, sweeps, float(np.max(np.abs(mine[r][k] - flds[r][k]))))
+
+
+@pytest.mark.parametrize("case", [dict(name="rbc_ppn_tanhz", xInd=4, yInd=3, zInd=4, vcDepth=2, xPer=1, yPer=1, zGrid=2, betaZ=1.3, prob=5),
+                                  dict(name="rbc_nnn", xInd=3, yInd=4, zInd=4, vcDepth=2, prob=5),
+                                  dict(name="rbc_ppp", xInd=4, yInd=4, zInd=3, vcDepth=2, xPer=1, yPer=1, zPer=1, prob=5)], ids=lambda c: c["name"])
+def test_temperature_solve_matches_the_reference(case):
+    """scalar_d3::solveT (with its ztz2Colloc quirk and the fxMax index ranges) against implo_solve_T"""
+    dt, tol, Ra, Pr = 0.02, 1e-5, 1.0e3, 0.5
+    o, _ = _mk(case)
+    p = sarasts.params(o.cfg, prob_type=5, dt=dt, cn_tolerance=tol, scalar=True, rbc_type=2, force_type=3, Ra=Ra, Pr=Pr)
+    ext = sarasts.extents(p)
+    rng = np.random.default_rng(8)
+    flds = [{"T": np.ascontiguousarray(rng.uniform(0, 1, ext["T"])), "rhs_T": np.ascontiguousarray(rng.uniform(0, 1, ext["rhs_T"]))}]
+    mine = {k: a.copy() for k, a in flds[0].items()}
+    sarasts.run(p, sarasts.SOLVE_T, flds)
+    kappa = 1.0 / np.sqrt(Pr * Ra)                      # scalar.cc:76-78, RBC Type 2
+    t, v = mo.temperature_bcs(o.cfg["xPer"], o.cfg["yPer"], o.cfg["zPer"], 5)
+    sweeps, err = mo.solve_temperature(o, dt, kappa, tol, t, v, mine["T"], mine["rhs_T"])
+    assert sweeps > 2 and err < tol
+    assert np.array_equal(mine["T"], flds[0]["T"]), (sweeps, float(np.max(np.abs(mine["T"] - flds[0]["T"]))))
