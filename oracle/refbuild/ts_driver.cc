@@ -18,6 +18,7 @@
  *   mode 4  modes 3, 0, mgSolve, 1, 2 in sequence: the tail of timeAdvance from nseRHS on               :303-366
  *   mode 6  nseRHS = 0; V.computeDiff(nseRHS);  (returned in the nseRHS slots)                          :259-265
  *   mode 7  nSteps x timeAdvance() from the configured initial condition (inputs given replace it)      :254-367
+ *   mode 9  nseRHS = 0; V.computeNLin(V, nseRHS);  (returned in the nseRHS slots)                       :268-277
  *   mode 8  scalar_d3::solveT() on the given T and tmpRHS                                     scalar_d3.cc:541-594
  * Fields go in and out as the padded Blitz arrays of every rank.  Ranks are threads (mpi-lite).
  */
@@ -111,6 +112,7 @@ void run_solver(Job *job, const grid &gridData, const parser &inputParams, paral
     for (int q = 0; q < 11; q++) if (dst[q] && !((p.outputOnly >> q) & 1)) put(*dst[q], F.f[q]);
     const int m = job->mode;
     if (m == 6) { H.nseRHS = 0.0; H.V.computeDiff(H.nseRHS); }
+    if (m == 9) { H.nseRHS = 0.0; H.V.computeNLin(H.V, H.nseRHS); }  /* the convective term alone, hydro_d3.cc:268-277 */
     if (m == 8) solve_t(H);                                         /* scalar_d3::solveT(), scalar_d3.cc:541-594 */
     if (m == 7) for (int n = 0; n < p.nSteps; n++) H.timeAdvance();
     if (m == 3 || m == 4) { H.solveVx(); H.solveVy(); H.solveVz(); }

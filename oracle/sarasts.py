@@ -9,7 +9,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "libsarasts_d3.so")
-DIVERGENCE, CORRECTION, IMPOSE_BCS, IMPLICIT, STEP_TAIL, MGSOLVE, COMPUTE_DIFF, TIME_ADVANCE, SOLVE_T = range(9)
+DIVERGENCE, CORRECTION, IMPOSE_BCS, IMPLICIT, STEP_TAIL, MGSOLVE, COMPUTE_DIFF, TIME_ADVANCE, SOLVE_T, COMPUTE_NLIN = range(10)
 FIELDS = ("vx", "vy", "vz", "P", "Pp", "mgRHS", "rhs_x", "rhs_y", "rhs_z", "T", "rhs_T")
 
 

@@ -455,7 +455,7 @@ template <class T, int N> Array<T, N> pow2(const Array<T, N> &a) { return a.map(
  * i.e. the stencil expression's domain is the operand's domain shrunk by one point at each end of `dim` -- where both
  * neighbours exist -- and it is assigned, position by position, to a destination view of exactly that shape.  Returned here as
  * a compact array of the shrunk shape whose element p along `dim` is the stencil applied at operand index lbound + 1 + p
- * (central12n: A(+1) - A(-1); central22n: A(+1) - 2 A + A(-1), in that order).  Not on any path this repository pins bit for
+ * (central12n: (A(+1) - A(-1)) / 2; central22n: A(-1) - 2 A + A(+1), in that order).  Not on any path this repository pins bit for
  * bit (computeDiff / computeNLin); tests/test_reference_timestep.py checks them against analytic derivatives. */
 template <class T, class F>
 Array<T, 3> stencil3_(const Array<T, 3> &a, int dim, F f) {
@@ -472,10 +472,12 @@ Array<T, 3> stencil3_(const Array<T, 3> &a, int dim, F f) {
     }
     return r;
 }
+/* the `n` variants are Blitz's NORMALISED stencils: central12 = A(+1) - A(-1) has the factor 2 h, so central12n = central12 / 2 (the
+ * reference multiplies by 1/h only, derivative.cc:122-123); central22 = A(-1) - 2 A + A(+1) has the factor h^2, central22n = central22 */
 template <class T>
-Array<T, 3> central12n(const Array<T, 3> &a, int dim) { return stencil3_(a, dim, [](const T &p, const T &, const T &m) { return p - m; }); }
+Array<T, 3> central12n(const Array<T, 3> &a, int dim) { return stencil3_(a, dim, [](const T &p, const T &, const T &m) { return (p - m) * T(0.5); }); }
 template <class T>
-Array<T, 3> central22n(const Array<T, 3> &a, int dim) { return stencil3_(a, dim, [](const T &p, const T &c, const T &m) { return p - T(2) * c + m; }); }
+Array<T, 3> central22n(const Array<T, 3> &a, int dim) { return stencil3_(a, dim, [](const T &p, const T &c, const T &m) { return m - T(2) * c + p; }); }
 
 /* ---- full reductions ---- */
 template <class T, int N>

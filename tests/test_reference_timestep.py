@@ -52,6 +52,40 @@ def test_reference_compute_diff_converges_to_the_analytic_laplacian():
 
 
 @needs_ts
+def test_reference_convective_term_converges_to_the_analytic_one():
+    """vfield::computeNLin of the Taylor-Green velocity field, x component: -(u u_x + v u_y + w u_z) to second order.  This is
+    the check of the NORMALISED first-derivative stencil (central12n = (A(+1) - A(-1)) / 2): without the 1/2 the ratio to the
+    analytic term would tend to 2, not 1."""
+    L = 2.0 * np.pi
+    errs = []
+    for ind in (4, 5, 6):
+        o = Oracle(dim=3, xInd=ind, yInd=ind, zInd=ind, vcDepth=2, xPer=1, yPer=1, zPer=1, Lx=L, Ly=L, Lz=L)
+        p = sarasts.params(o.cfg, prob_type=5, dt=0.001, Re=100.0)
+        ext = sarasts.extents(p)
+        h = L / (1 << ind)
+
+        def coords(shape, comp):
+            c = [((np.arange(-1, shape[d] - 1) + 0.5) * h if d == comp else np.arange(-1, shape[d] - 1) * h) for d in range(3)]
+            return np.meshgrid(*c, indexing="ij")
+
+        f = {}
+        X, Y, Z = coords(ext["vx"], 0)
+        f["vx"] = np.ascontiguousarray(np.sin(X) * np.cos(Y) * np.cos(Z))
+        X, Y, Z = coords(ext["vy"], 1)
+        f["vy"] = np.ascontiguousarray(-np.cos(X) * np.sin(Y) * np.cos(Z))
+        f["vz"] = np.zeros(ext["vz"])
+        for nm in ("rhs_x", "rhs_y", "rhs_z"):
+            f[nm] = np.zeros(ext[nm])
+        sarasts.run(p, sarasts.COMPUTE_NLIN, [f])
+        X, Y, Z = coords(ext["vx"], 0)
+        conv = (np.sin(X) * np.cos(Y) * np.cos(Z)) * (np.cos(X) * np.cos(Y) * np.cos(Z)) + \
+               (-np.cos(X) * np.sin(Y) * np.cos(Z)) * (-np.sin(X) * np.sin(Y) * np.cos(Z))
+        core = (slice(2, -2),) * 3
+        errs.append(float(np.abs(f["rhs_x"][core] + conv[core]).max() / np.abs(conv).max()))
+    assert errs[0] < 0.08 and 3.5 < errs[0] / errs[1] < 4.5 and 3.5 < errs[1] / errs[2] < 4.5, errs
+
+
+@needs_ts
 def test_reference_taylor_green_steps_are_physical():
     """hydro_d3::timeAdvance x 3 from the reference's own Taylor-Green initial condition (Re = 100, 2 pi box): divergence-free
     start, kinetic energy decaying as exp(-2 nu k^2 t) with k^2 = 3 (the nonlinear term only redistributes energy at this
