@@ -9,6 +9,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "libsarasts_d3.so")
+DROPIN_LIB = os.path.join(_HERE, "_ref", "libsarastsdropin_d3.so")     # the same time stepper linked against THIS repository's drop-in poisson class (needs a GPU to run)
 DIVERGENCE, CORRECTION, IMPOSE_BCS, IMPLICIT, STEP_TAIL, MGSOLVE, COMPUTE_DIFF, TIME_ADVANCE, SOLVE_T, COMPUTE_NLIN = range(10)
 FIELDS = ("vx", "vy", "vz", "P", "Pp", "mgRHS", "rhs_x", "rhs_y", "rhs_z", "T", "rhs_T")
 
@@ -26,21 +27,21 @@ class RankFields(C.Structure):
     _fields_ = [("f", C.POINTER(C.c_double) * 11)]
 
 
-def available():
-    return os.path.exists(LIB)
+def available(dropin=False):
+    return os.path.exists(DROPIN_LIB if dropin else LIB)
 
 
-_lib = None
+_libs = {}
 
 
-def _load():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(LIB)
-        _lib.sarasts_extents.argtypes = [C.POINTER(TsParams), C.POINTER(C.c_int)]
-        _lib.sarasts_run.argtypes = [C.c_char_p, C.POINTER(TsParams), C.POINTER(RankFields), C.c_int]
-        _lib.sarasts_run.restype = C.c_int
-    return _lib
+def _load(dropin=False):
+    if dropin not in _libs:
+        lib = C.CDLL(DROPIN_LIB if dropin else LIB)
+        lib.sarasts_extents.argtypes = [C.POINTER(TsParams), C.POINTER(C.c_int)]
+        lib.sarasts_run.argtypes = [C.c_char_p, C.POINTER(TsParams), C.POINTER(RankFields), C.c_int]
+        lib.sarasts_run.restype = C.c_int
+        _libs[dropin] = lib
+    return _libs[dropin]
 
 
 def params(cfg, prob_type=1, Re=1000.0, dt=0.01, cn_tolerance=1e-6, ic_type=0, n_steps=1, output_only=(), scalar=False, rbc_type=2,
@@ -57,18 +58,19 @@ def params(cfg, prob_type=1, Re=1000.0, dt=0.01, cn_tolerance=1e-6, ic_type=0, n
     return p
 
 
-def extents(p):
+def extents(p, dropin=False):
     out = (C.c_int * 33)()
-    _load().sarasts_extents(C.byref(p), out)
+    _load(dropin).sarasts_extents(C.byref(p), out)
     return {name: tuple(out[3 * q:3 * q + 3]) for q, name in enumerate(FIELDS)}
 
 
-def run(p, mode, fields):
+def run(p, mode, fields, dropin=False):
     """fields: list (one entry per rank) of dicts name -> C-contiguous float64 array in the field's padded layout; arrays of
-    are overwritten with the reference's results (all nine, when given); missing entries keep the constructor's values."""
+    are overwritten with the reference's results (all of them, when given); missing entries keep the constructor's values.
+    dropin=True: the same time stepper with this repository's drop-in poisson class (CUDA) in place of the reference's lib/poisson."""
     nr = p.npX * p.npY
     assert len(fields) == nr
-    ext = extents(p)
+    ext = extents(p, dropin)
     arr = (RankFields * nr)()
     for r, d in enumerate(fields):
         for q, name in enumerate(FIELDS):
@@ -79,6 +81,6 @@ def run(p, mode, fields):
             assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.shape == ext[name], (name, a.shape, ext[name])
             arr[r].f[q] = a.ctypes.data_as(C.POINTER(C.c_double))
     with tempfile.TemporaryDirectory() as wd:
-        rc = _load().sarasts_run(wd.encode(), C.byref(p), arr, int(mode))
+        rc = _load(dropin).sarasts_run(wd.encode(), C.byref(p), arr, int(mode))
     if rc != 0:
         raise RuntimeError("sarasts_run failed")
